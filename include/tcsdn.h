@@ -1,0 +1,146 @@
+/*
+ * tcsdn.h -- C ABI of libtcsdn.so: B200 (sm_100a) kernels for the per-flow classification path of
+ * ashwinn-v/Traffic-classifier-SDN.
+ *
+ * What this boundary replaces.  The reference has no FFI; its hot path is two Python statements:
+ *     model = pickle.load(infile)                       reference traffic_classifier.py:243
+ *     label = model.predict(features.tolist())          reference traffic_classifier.py:106
+ * where `model` is one of six scikit-learn estimators (traffic_classifier.py:229-240).  Each
+ * `tcsdn_*_create` below takes the fitted attributes of one of those estimators (the state that
+ * pickle.load yields) and each `tcsdn_predict` call is one `model.predict(X)`: rows in, one class
+ * index per row out (+ the estimator's score matrix on request).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is caller-owned; the library never frees or keeps
+ *     caller memory after a call returns (create() copies parameters to HBM).
+ *   - every function returns 0 on success or a negative TCSDN_E* code; tcsdn_last_error() returns a
+ *     thread-local, NUL-terminated description of the last failure in the calling thread.
+ *   - nothing here throws, aborts or calls exit().  There is no CPU fallback: without a CUDA device
+ *     every create/predict fails with TCSDN_ECUDA.
+ *   - handles are immutable after create; predict on one handle from several host threads is safe
+ *     (per-call scratch comes from a mutex-guarded pool inside the handle).
+ *   - rows are row-major, contiguous [n][d], float32 or float64, in host or device memory.
+ *     labels_out has n int32.  scores_out (nullable) has n*tcsdn_model_score_cols() float64 and
+ *     lives where X lives.  With device pointers the call only enqueues work on `stream`; with host
+ *     pointers it returns when labels_out/scores_out are filled.
+ */
+#ifndef TCSDN_H
+#define TCSDN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCSDN_VERSION 100 /* 0.1.0 */
+
+typedef struct tcsdn_model tcsdn_model_t;
+
+enum { TCSDN_F32 = 0, TCSDN_F64 = 1 };     /* x_dtype */
+enum { TCSDN_HOST = 0, TCSDN_DEVICE = 1 }; /* x_loc: where X, labels_out and scores_out live */
+
+enum {
+    TCSDN_OK = 0,
+    TCSDN_EINVAL = -1,    /* bad argument (shape, dtype, NULL, unsupported option) */
+    TCSDN_ECUDA = -2,     /* CUDA runtime/driver error, or no device */
+    TCSDN_ENOMEM = -3,    /* host or device allocation failed */
+    TCSDN_ENONFINITE = -4 /* X holds NaN or +-inf (sklearn's validate_data raises ValueError) */
+};
+
+enum { /* tcsdn_model_kind() */
+    TCSDN_KIND_LINEAR = 1, TCSDN_KIND_GNB = 2, TCSDN_KIND_KMEANS = 3,
+    TCSDN_KIND_KNN = 4, TCSDN_KIND_SVC = 5, TCSDN_KIND_FOREST = 6
+};
+
+enum { /* tcsdn_set_option() keys */
+    TCSDN_OPT_ENGINE = 1,      /* 0 auto, 1 force the fp64 CUDA-core kernels, 2 force the tensor-core engine */
+    TCSDN_OPT_CHUNK_ROWS = 2,  /* host-pointer pipeline chunk (rows); 0 = default */
+    TCSDN_OPT_CHECK_FINITE = 3 /* 1 (default): fail with TCSDN_ENONFINITE on NaN/inf input */
+};
+
+int tcsdn_version(void);
+const char *tcsdn_last_error(void);
+int tcsdn_device_count(int32_t *count_out);
+int tcsdn_set_device(int32_t device);           /* device for subsequent create() calls of this thread */
+int tcsdn_device_sm_count(int32_t *sms_out);
+
+/* ---- model import: the state `pickle.load` yields at traffic_classifier.py:243 ----------------- */
+
+/* LogisticRegression: coef_ [n_rows][d], intercept_ [n_rows]; n_rows == 1 is the binary case
+ * (label = score > 0).  sk:linear_model/_base.py:366-427. */
+int tcsdn_linear_create(const double *coef, const double *intercept, int32_t n_rows, int32_t d,
+                        tcsdn_model_t **out);
+
+/* GaussianNB: theta_, var_ [n_classes][d] (var_ already holds epsilon_), class_prior_ [n_classes].
+ * sk:naive_bayes.py:96-117,533-545. */
+int tcsdn_gnb_create(const double *theta, const double *var, const double *class_prior,
+                     int32_t n_classes, int32_t d, tcsdn_model_t **out);
+
+/* KMeans: cluster_centers_ [k][d].  sk:cluster/_k_means_lloyd.pyx:168-213. */
+int tcsdn_kmeans_create(const double *centers, int32_t k, int32_t d, tcsdn_model_t **out);
+
+/* KNeighborsClassifier(weights='uniform', euclidean): _fit_X [n_train][d], _y [n_train] class index
+ * in [0,n_classes).  sk:neighbors/_classification.py:245-312, sk:utils/_heap.pyx:6-88. */
+int tcsdn_knn_create(const double *fit_x, const int32_t *y, int64_t n_train, int32_t d,
+                     int32_t n_classes, int32_t k, tcsdn_model_t **out);
+
+/* SVC(kernel='rbf'): support_vectors_ [n_sv][d] grouped by class, _dual_coef_ [n_classes-1][n_sv],
+ * _intercept_ [n_classes*(n_classes-1)/2], _n_support [n_classes], _gamma.
+ * sk:svm/src/libsvm/svm.cpp:461-478,2846-2904; sk:svm/src/libsvm/libsvm_helper.c:171. */
+int tcsdn_svc_create(const double *sv, const double *dual_coef, const double *intercept,
+                     const int32_t *n_support, int32_t n_sv, int32_t d, int32_t n_classes,
+                     double gamma, tcsdn_model_t **out);
+
+/* RandomForestClassifier: trees concatenated; tree t owns nodes [tree_offsets[t], tree_offsets[t+1]);
+ * left/right are node indices local to the tree (-1 = leaf); value [n_nodes][n_classes] are the
+ * per-node class fractions DecisionTreeClassifier.predict_proba returns.
+ * sk:tree/_tree.pyx:954-996, sk:ensemble/_forest.py:606-624,704-716,882-967. */
+int tcsdn_forest_create(const int64_t *tree_offsets, const int32_t *left, const int32_t *right,
+                        const int32_t *feature, const double *threshold, const double *value,
+                        int32_t n_trees, int32_t d, int32_t n_classes, tcsdn_model_t **out);
+
+void tcsdn_destroy(tcsdn_model_t *m);
+
+int tcsdn_model_kind(const tcsdn_model_t *m);
+int tcsdn_model_n_features(const tcsdn_model_t *m);
+/* columns of scores_out: linear n_rows (decision_function), gnb n_classes (joint log likelihood),
+ * kmeans k (||c||^2 - 2 x.c), knn n_classes (neighbour votes / k), svc n_classes*(n_classes-1)/2
+ * (libsvm's one-vs-one decision values), forest n_classes (predict_proba). */
+int tcsdn_model_score_cols(const tcsdn_model_t *m);
+int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value);
+/* counters of the last predict on this handle: [0] kernels launched, [1] rows through the tensor-core
+ * engine, [2] rows through the fp64 CUDA-core kernels, [3] exact re-evaluations (knn), [4] node visits
+ * (forest, only when profiling is on), rest reserved.  out has 8 slots. */
+int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
+
+/* ---- the hot call: one model.predict(X)  (traffic_classifier.py:106) ---------------------------- */
+int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t x_dtype,
+                  int32_t x_loc, int32_t *labels_out, double *scores_out, void *cuda_stream);
+
+/* After device-pointer predicts: synchronise `cuda_stream` and report TCSDN_ENONFINITE if any of them saw
+ * NaN/inf rows (host-pointer predicts do this themselves). */
+int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream);
+
+/* SVC.decision_function(decision_function_shape='ovr'): votes + conf/(3(|conf|+1)) from the OvO values
+ * (sk:utils/multiclass.py:557-599).  dec [n][P], out [n][n_classes]; both where `loc` says. */
+int tcsdn_svc_ovr_from_ovo(const double *dec, int64_t n, int32_t n_classes, int32_t loc, double *out,
+                           void *cuda_stream);
+
+/* ---- N1 (next row): Flow.updateforward/updatereverse on device ----------------------------------
+ * reference traffic_classifier.py:63-96,104.  One call applies one poll to n flows.
+ * state [n][TCSDN_FLOW_STATE] float64 (device), layout per direction:
+ *   packets, bytes, delta_packets, delta_bytes, inst_pps, avg_pps, inst_bps, avg_bps, last_time
+ * forward block first, reverse block second, then time_start.  packets/bytes/curr_time [n] float64
+ * cumulative counters; dir [n] uint8: 0 forward, 1 reverse, 2 no sample this poll.
+ * features_out (nullable) [n][12] float32 or float64 in the order of traffic_classifier.py:104. */
+#define TCSDN_FLOW_STATE 19
+int tcsdn_flow_update(double *state, const double *packets, const double *bytes,
+                      const double *curr_time, const uint8_t *dir, int64_t n, void *features_out,
+                      int32_t feat_dtype, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCSDN_H */

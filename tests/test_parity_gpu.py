@@ -1,0 +1,333 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+  (a) tests/golden/bundled.npz -- sklearn's answers for the reference's six pickles on its bundled rows,
+  (b) the CPU oracle (oracle/tcsdn_oracle.c) on seeded inputs and edge cases,
+  (c) live scikit-learn (installed on the box; the library the reference calls) on fresh fits,
+  (d) size-independent properties at BASELINE sizes.
+Bars: class indices bit-exact everywhere; RandomForest probabilities and KNN votes bit-exact; LR / NB /
+KMeans scores <= 1e-12 relative; SVC decision values <= 1e-9 absolute with the fp64 kernel.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import KINDS
+from sk_rebuild import quiet
+from traffic_classifier_sdn_b200 import _lib, from_sklearn, from_spec, synth
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = {"linear": 1e-12, "gnb": 1e-12, "kmeans": 1e-12, "knn": 0.0, "svc": 1e-9, "forest": 0.0}
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def models(specs):
+    return {k: from_spec(specs[k]) for k in KINDS}
+
+
+# ------------------------------------------------------------------ (a) golden vectors
+@pytest.mark.parametrize("kind", KINDS)
+def test_golden_labels_and_scores_f64_host(golden, specs, models, kind):
+    X = golden["X"]
+    idx, sc = models[kind]._run(X, True)
+    assert np.array_equal(idx, golden[f"{kind}.expected_label"])
+    exp = golden[f"{kind}.expected_score"]
+    if kind == "knn":
+        assert np.array_equal(np.rint(sc * 5).astype(np.uint8), exp)
+    elif kind == "forest":
+        assert np.array_equal(sc, exp)
+    elif kind == "kmeans":
+        d2 = sc + np.einsum("ij,ij->i", X, X)[:, None]
+        assert np.max(np.abs(d2 - exp ** 2) / np.maximum(1.0, exp ** 2)) < 1e-6
+    elif kind == "svc":
+        assert np.max(np.abs(sc - exp)) < 1e-9
+    else:
+        assert rel_err(sc, exp) < SCORE_TOL[kind]
+    # and the public sklearn-like surface
+    pred = models[kind].predict(X[:50])
+    if kind == "kmeans":
+        assert pred.dtype == np.int32 and np.array_equal(pred, idx[:50])
+    else:
+        assert np.array_equal(pred, np.asarray(specs[kind]["classes"])[idx[:50]])
+
+
+def test_svc_decision_function_ovr(golden, models):
+    ovr = models["svc"].decision_function(golden["X"])
+    assert np.max(np.abs(ovr - golden["svc.expected_ovr"])) < 1e-9
+
+
+def test_reference_call_pattern_one_row_list(golden, specs, models):
+    """traffic_classifier.py:106 -- predict(features.tolist()) with a single 1x12 row of Python floats."""
+    for kind in KINDS:
+        for i in (0, 1234, 7652):
+            row = golden["X"][i].reshape(1, -1).tolist()
+            lab = models[kind].predict(row)
+            exp = golden[f"{kind}.expected_label"][i]
+            assert lab.shape == (1,)
+            assert lab[0] == (exp if kind == "kmeans" else specs[kind]["classes"][exp])
+
+
+# ------------------------------------------------------------------ (b) oracle, dtypes, locations, edges
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 1024, 1025, 3000])
+def test_ragged_sizes_f32_host_vs_oracle(specs, models, kind, n):
+    X32 = synth.make_flows(n, seed=100 + n, dtype=np.float32, return_labels=False)
+    idx, sc = models[kind]._run(X32, True)
+    ref_idx, ref_sc = oracle.predict(specs[kind], X32.astype(np.float64))
+    assert np.array_equal(idx, ref_idx)
+    if SCORE_TOL[kind] == 0.0:
+        assert np.array_equal(sc, ref_sc)
+    elif kind == "svc":
+        assert np.max(np.abs(sc - ref_sc)) < 1e-9
+    else:
+        assert rel_err(sc, ref_sc) < SCORE_TOL[kind]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_device_pointers_match_host_pointers(specs, models, kind):
+    import torch
+    X = synth.make_flows(5000, seed=5, return_labels=False)
+    for dt in (np.float32, np.float64):
+        Xh = X.astype(dt)
+        idx_h, sc_h = models[kind]._run(Xh, True)
+        idx_d, sc_d = models[kind]._run(torch.from_numpy(Xh).cuda(), True)
+        models[kind].sync_check()
+        assert idx_d.is_cuda and np.array_equal(idx_d.cpu().numpy(), idx_h)
+        assert np.array_equal(sc_d.cpu().numpy(), sc_h)
+
+
+def test_empty_batch(models):
+    for kind in KINDS:
+        out = models[kind].predict(np.empty((0, 12)))
+        assert out.shape == (0,)
+
+
+def test_wrong_feature_count_and_nonfinite_raise(models):
+    for kind in KINDS:
+        with pytest.raises(ValueError, match="features"):
+            models[kind].predict(np.zeros((3, 11)))
+        bad = np.ones((700, 12))
+        bad[513, 4] = np.nan
+        with pytest.raises(ValueError, match="NaN|infinity"):
+            models[kind].predict(bad)
+        bad[513, 4] = np.inf
+        with pytest.raises(ValueError, match="NaN|infinity"):
+            models[kind].predict(bad.astype(np.float32))
+        with pytest.raises(ValueError, match="2D"):
+            models[kind].predict(np.zeros(12))
+        assert models[kind].predict(np.ones((2, 12))).shape == (2,)  # still usable afterwards
+
+
+def test_unaligned_host_pointer_and_chunked_pipeline(specs, models):
+    X = synth.make_flows(20000, seed=9, dtype=np.float32, return_labels=False)
+    buf = np.empty(X.size + 1, np.float32)
+    view = buf[1:].reshape(X.shape)   # 4-byte aligned only
+    view[:] = X
+    for kind in ("linear", "gnb", "forest"):
+        ref = models[kind]._run(X, False)[0]
+        assert np.array_equal(models[kind]._run(view, False)[0], ref)
+        models[kind].set_option(_lib.OPT_CHUNK_ROWS, 3000)   # 7 chunks through the double-buffered pipeline
+        assert np.array_equal(models[kind]._run(X, False)[0], ref)
+        models[kind].set_option(_lib.OPT_CHUNK_ROWS, 0)
+
+
+def test_inputs_not_modified_and_outputs_fresh(models):
+    X = synth.make_flows(300, seed=2, return_labels=False)
+    X0 = X.copy()
+    a = models["forest"].predict(X)
+    b = models["forest"].predict(X)
+    assert np.array_equal(X, X0) and a is not b and np.array_equal(a, b)
+
+
+def test_not_fitted_raises():
+    from traffic_classifier_sdn_b200 import GaussianNB, NotFittedError
+    with pytest.raises(NotFittedError):
+        GaussianNB().predict(np.zeros((1, 12)))
+
+
+# ------------------------------------------------------------------ generic shapes (d, classes outside the fast path)
+def test_scorers_generic_shapes_vs_oracle():
+    rng = np.random.default_rng(0)
+    for d, R in ((5, 3), (12, 11), (20, 4), (8, 1), (12, 1), (16, 8), (4, 2)):
+        X = rng.normal(0, 30, (2000, d))
+        lin = dict(kind="linear", coef=rng.normal(0, 1, (R, d)), intercept=rng.normal(0, 1, R),
+                   classes=np.arange(max(R, 2)), n_features=d)
+        nb = dict(kind="gnb", theta=rng.normal(0, 20, (max(R, 2), d)), var=rng.random((max(R, 2), d)) * 50 + 0.1,
+                  class_prior=np.full(max(R, 2), 1.0 / max(R, 2)), classes=np.arange(max(R, 2)), n_features=d)
+        km = dict(kind="kmeans", centers=rng.normal(0, 30, (max(R, 2), d)), classes=np.arange(max(R, 2)), n_features=d)
+        for spec in (lin, nb, km):
+            est = from_spec(spec)
+            for Xi in (X, X.astype(np.float32)):
+                idx, sc = est._run(Xi, True)
+                ridx, rsc = oracle.predict(spec, Xi.astype(np.float64))
+                assert np.array_equal(idx, ridx), (spec["kind"], d, R)
+                assert rel_err(sc, rsc) < 1e-12
+
+
+# ------------------------------------------------------------------ forest: groups, oversize trees, impure leaves, fp32 rounding
+@pytest.mark.parametrize("cfg", [dict(n_trees=40, depth=11, full=True), dict(n_trees=3, depth=15, full=True),
+                                 dict(n_trees=100, depth=16, full=False), dict(n_trees=7, depth=3, full=True)])
+def test_forest_synthetic_vs_oracle(cfg):
+    spec = synth.random_forest_spec(seed=4, impure=0.2, **cfg)
+    est = from_spec(spec)
+    X = synth.make_flows(6000, seed=8, return_labels=False)
+    X[::7] += 1e-6   # values that are not fp32-representable: exercises the float32 cast + floor32 thresholds
+    idx, pr = est._run(X, True)
+    ridx, rpr = oracle.forest(spec, X)
+    assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+    idx32, pr32 = est._run(X.astype(np.float32), True)
+    assert np.array_equal(pr32, rpr)
+
+
+def test_forest_threshold_boundary_values():
+    """rows sitting exactly on thresholds and one ulp either side (in fp32) go the way sklearn sends them"""
+    spec = synth.random_forest_spec(n_trees=5, depth=6, seed=1, full=True, impure=0.3)
+    thr = spec["threshold"][spec["left"] >= 0]
+    f = spec["feature"][spec["left"] >= 0]
+    rows = []
+    for t, j in zip(thr[:150], f[:150]):
+        for v in (np.float32(t), np.nextafter(np.float32(t), np.float32(np.inf)), np.nextafter(np.float32(t), np.float32(-np.inf)), t):
+            r = np.zeros(12)
+            r[j] = v
+            rows.append(r)
+    X = np.asarray(rows)
+    est = from_spec(spec)
+    idx, pr = est._run(X, True)
+    ridx, rpr = oracle.forest(spec, X)
+    assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+
+
+# ------------------------------------------------------------------ knn: ties
+def test_knn_lattice_ties_match_sklearn_heap_semantics():
+    rng = np.random.default_rng(7)
+    tr = np.floor(rng.random((900, 4)) * 3)
+    y = rng.integers(0, 5, 900).astype(np.int32)
+    q = np.floor(rng.random((3000, 4)) * 3)
+    spec = dict(kind="knn", fit_X=tr, y=y, k=5, classes=np.arange(5), n_features=4)
+    est = from_spec(spec)
+    idx, pr = est._run(q, True)
+    ridx, rpr = oracle.knn(spec, q)
+    assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+    from sklearn.neighbors import KNeighborsClassifier
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):
+        sk = KNeighborsClassifier(5, algorithm="brute").fit(tr, y)
+        assert np.array_equal(pr, sk.predict_proba(q))
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 17])
+def test_knn_k_values_vs_oracle(k):
+    Xt, yt = synth.make_flows(3000, seed=21)
+    Xq = synth.make_flows(1500, seed=22, return_labels=False)
+    Xq[:200] = Xt[:200]  # exact duplicates of training rows
+    spec = dict(kind="knn", fit_X=Xt, y=yt, k=k, classes=synth.CLASSES, n_features=12)
+    est = from_spec(spec)
+    idx, pr = est._run(Xq, True)
+    ridx, rpr = oracle.knn(spec, Xq)
+    assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+
+
+# ------------------------------------------------------------------ (c) fresh fits vs live scikit-learn
+def test_fresh_fits_on_bundled_rows_vs_sklearn(golden):
+    """notebook recipe: train_test_split(test_size=0.5, random_state=101), default constructors"""
+    from sklearn.cluster import KMeans
+    from sklearn.ensemble import RandomForestClassifier
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import train_test_split
+    from sklearn.naive_bayes import GaussianNB
+    from sklearn.neighbors import KNeighborsClassifier
+    from sklearn.svm import SVC
+    from threadpoolctl import threadpool_limits
+    X, y = golden["X"], golden["y"]
+    Xtr, Xte, ytr, yte = train_test_split(X, y, test_size=0.5, random_state=101)
+    fits = [quiet(LogisticRegression().fit, Xtr, ytr), GaussianNB().fit(Xtr, ytr),
+            KMeans(5, n_init=3, random_state=0).fit(Xtr), KNeighborsClassifier(algorithm="brute").fit(Xtr, ytr),
+            SVC().fit(Xtr, ytr), RandomForestClassifier(random_state=0).fit(Xtr, ytr)]
+    for sk in fits:
+        est = from_sklearn(sk)
+        with threadpool_limits(limits=1):
+            exp = quiet(sk.predict, X)
+        got = est.predict(X)
+        assert np.array_equal(got, exp), type(sk).__name__
+        if hasattr(sk, "predict_proba") and type(sk).__name__ in ("RandomForestClassifier", "KNeighborsClassifier"):
+            with threadpool_limits(limits=1):
+                assert np.array_equal(est.predict_proba(X), quiet(sk.predict_proba, X))
+    assert est.score(Xte, yte) > 0.99  # the forest, like notebook cell 17
+
+
+def test_estimator_fit_route(golden):
+    from traffic_classifier_sdn_b200 import GaussianNB, RandomForestClassifier
+    X, y = golden["X"], golden["y"]
+    nb = GaussianNB().fit(X, y)
+    assert nb.score(X, y) > 0.95 and list(nb.classes_) == sorted(set(y))
+    rf = RandomForestClassifier(n_estimators=10, random_state=0).fit(X, y)
+    assert rf.predict_proba(X[:10]).shape == (10, 5)
+
+
+# ------------------------------------------------------------------ (d) BASELINE-size properties
+def test_large_batch_properties_scorers_and_forest(specs, models):
+    """2M rows: permutation equivariance, agreement between one big launch and 16 slices, oracle on a sample."""
+    import torch
+    n = 2_000_000
+    base = synth.make_flows(250_000, seed=77, dtype=np.float32, return_labels=False)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    pick = torch.randint(0, len(base), (n,), generator=g)
+    X = torch.from_numpy(base)[pick].cuda()
+    perm = torch.randperm(n, generator=g).cuda()
+    for kind in ("linear", "gnb", "kmeans", "forest"):
+        full = models[kind].predict_indices(X)
+        permuted = models[kind].predict_indices(X[perm].contiguous())
+        assert torch.equal(full[perm], permuted)
+        parts = torch.cat([models[kind].predict_indices(c.contiguous()) for c in X.chunk(16)])
+        assert torch.equal(full, parts)
+        models[kind].sync_check()
+        s = slice(0, n, 997)
+        ref = oracle.predict(specs[kind], X[s].cpu().numpy().astype(np.float64), want_scores=False)[0]
+        assert np.array_equal(full[s].cpu().numpy(), ref)
+        # label histogram is a checksum of checksums: equal to the histogram of the base rows weighted by picks
+        base_lab = oracle.predict(specs[kind], base.astype(np.float64), want_scores=False)[0]
+        exp_hist = np.bincount(base_lab[pick.numpy()], minlength=8)
+        assert np.array_equal(np.bincount(full.cpu().numpy(), minlength=8), exp_hist)
+
+
+# ------------------------------------------------------------------ N1: feature derivation on device
+def test_flow_update_kernel_matches_host_formulas():
+    import torch
+    from traffic_classifier_sdn_b200 import flows
+    rng = np.random.default_rng(5)
+    n = 5000
+    state = np.zeros((n, flows.STATE))
+    t0 = rng.integers(1000, 2000, n).astype(float)
+    state[:, flows.T0] = t0
+    state[:, flows.FWD + 8] = t0
+    state[:, flows.REV + 8] = t0
+    state[:, flows.FWD + 0] = rng.integers(0, 50, n)
+    state[:, flows.FWD + 1] = state[:, flows.FWD + 0] * 100
+    host = state.copy()
+    dstate = torch.from_numpy(state).cuda()
+    lib = _lib.load()
+    now = t0.copy()
+    for step in range(6):
+        now = now + rng.integers(0, 3, n)   # repeated timestamps hit the `!=` guards
+        direction = rng.integers(0, 3, n).astype(np.uint8)
+        dp = rng.integers(0, 40, n) * (rng.random(n) < 0.7)
+        cum_p = np.where(direction == 0, host[:, flows.FWD], host[:, flows.REV]) + dp
+        cum_b = np.where(direction == 0, host[:, flows.FWD + 1], host[:, flows.REV + 1]) + dp * rng.integers(60, 1500, n)
+        for i in range(n):
+            if direction[i] < 2:
+                blk = host[i, flows.REV:flows.REV + 9] if direction[i] else host[i, flows.FWD:flows.FWD + 9]
+                flows.update_direction(blk, host[i, flows.T0], cum_p[i], cum_b[i], now[i])
+        feats = torch.empty((n, 12), dtype=torch.float64, device="cuda")
+        args = [torch.from_numpy(a.astype(np.float64)).cuda() for a in (cum_p, cum_b, now)]
+        dd = torch.from_numpy(direction).cuda()
+        _lib.check(lib.tcsdn_flow_update(dstate.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(),
+                                         dd.data_ptr(), n, feats.data_ptr(), _lib.F64,
+                                         torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(dstate.cpu().numpy(), host)
+        assert np.array_equal(feats.cpu().numpy(), host[:, flows.FEATURE_COLUMNS])

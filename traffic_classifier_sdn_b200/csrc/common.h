@@ -1,0 +1,155 @@
+// common.h -- shared host-side declarations of libtcsdn (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/tcsdn.h"
+
+namespace tcsdn {
+
+void set_error(const char *fmt, ...);
+
+#define TCSDN_CUDA(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            tcsdn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                             __LINE__);                                                          \
+            return TCSDN_ECUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define TCSDN_TRY(expr)                \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != TCSDN_OK) return _r; \
+    } while (0)
+
+constexpr int kMaxClassesFast = 8;  // register-resident score paths are specialised up to here
+constexpr int kMaxClasses = 64;
+
+// Parameters of the streaming scorers, passed by value (__grid_constant__) so that fully unrolled
+// kernels read them as constant-bank operands.  a/b are [rows][d] (row stride d), c is [rows].
+//   linear : s_r = c_r + sum_j a_rj x_j                         (a = coef, c = intercept), argmax
+//   kmeans : s_r = c_r + sum_j a_rj x_j                         (a = -2 centers, c = ||c||^2), argmin
+//   gnb    : s_r = c_r + sum_j b_rj (x_j - a_rj)^2              (a = theta, b = -0.5/var), argmax
+struct ScorerParams {
+    double a[kMaxClassesFast * 16];
+    double b[kMaxClassesFast * 16];
+    double c[kMaxClassesFast];
+};
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Workspace {  // per-call scratch for the host-pointer pipeline
+    DeviceBuf x[2], labels[2], scores[2];
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int32_t *h_flag = nullptr;  // pinned
+    bool in_use = false;
+};
+
+}  // namespace tcsdn
+
+struct tcsdn_model {
+    int kind = 0;
+    int d = 0;
+    int dev = 0;
+    int n_classes = 0;   // rows of the score matrix for linear/gnb/kmeans; classes for knn/svc/forest
+    int score_cols = 0;
+    int sm_count = 148;
+    // options
+    int64_t opt_engine = 0;
+    int64_t opt_chunk_rows = 0;
+    int64_t opt_check_finite = 1;
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    // ---- streaming scorers
+    tcsdn::ScorerParams sp;          // valid when n_classes <= kMaxClassesFast && d <= 16
+    bool sp_valid = false;
+    double *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;  // same parameters in HBM (generic path)
+
+    // ---- knn
+    double *d_fit = nullptr;   // [n_train][d] f64
+    int32_t *d_y = nullptr;    // [n_train]
+    int64_t n_train = 0;
+    int k = 0;
+
+    // ---- svc
+    double *d_sv = nullptr;      // [n_sv][d]
+    double *d_coef = nullptr;    // [C-1][n_sv]
+    double *d_rho = nullptr;     // [P]  (= -intercept)
+    int32_t *d_start = nullptr;  // [C+1] class starts
+    int n_sv = 0;
+    double gamma = 0.0;
+
+    // ---- forest
+    uint2 *d_nodes = nullptr;        // packed preorder nodes, all trees
+    int32_t *d_tree_base = nullptr;  // [n_trees+1] node offset of each tree in d_nodes
+    int32_t *d_group_begin = nullptr;  // [n_groups+1] first tree of each smem group
+    double *d_leaf_val = nullptr;    // impure leaves: [n_impure][C]
+    int n_trees = 0, n_groups = 0;
+    int64_t n_nodes = 0;
+    int group_node_cap = 0;          // nodes that fit in the smem tree buffer
+    int max_group_nodes = 0;
+    bool forest_all_smem = false;    // every group fits in shared memory
+
+    // ---- per-handle misc
+    int32_t *d_flag = nullptr;       // device error flag (non-finite input)
+    std::mutex mu;
+    std::vector<tcsdn::Workspace *> pool;
+    void *engine = nullptr;          // tensor-core engine state (dist_engine.cu), may be null
+};
+
+namespace tcsdn {
+
+// kernels' host launchers (each enqueues on `st`, returns TCSDN_*).  x is a DEVICE pointer.
+int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                  cudaStream_t st);
+int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                  cudaStream_t st);
+int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                     cudaStream_t st);
+int launch_svc_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                     cudaStream_t st);
+int launch_ovr_from_ovo(const double *dec, int64_t n, int C, double *out, cudaStream_t st);
+int launch_flow_update(double *state, const double *packets, const double *bytes, const double *curr_time,
+                       const uint8_t *dir, int64_t n, void *features_out, int feat_dtype, cudaStream_t st);
+
+int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left, const int32_t *right,
+                const int32_t *feature, const double *threshold, const double *value, int n_trees, int C);
+
+// tensor-core distance engine (dist_engine.cu)
+int engine_create(tcsdn_model *m);   // builds packed operands for knn / svc handles
+void engine_destroy(tcsdn_model *m);
+bool engine_usable(const tcsdn_model *m, int64_t n);
+int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                  cudaStream_t st);
+
+template <typename T>
+int upload(T **dst, const T *src, size_t count) {
+    *dst = nullptr;
+    if (count == 0) return TCSDN_OK;
+    cudaError_t e = cudaMalloc((void **)dst, count * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? TCSDN_ENOMEM : TCSDN_ECUDA;
+    }
+    e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+        return TCSDN_ECUDA;
+    }
+    return TCSDN_OK;
+}
+
+}  // namespace tcsdn

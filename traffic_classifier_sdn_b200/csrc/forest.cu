@@ -1,0 +1,315 @@
+// forest.cu -- RandomForestClassifier.predict, bit-exact  (SURVEY 8a row a6).
+//
+//   sk:ensemble/_forest.py:606-624   X is cast to float32 before any tree sees it
+//   sk:tree/_tree.pyx:954-996        walk: (double)x[f] <= threshold ? left : right, until a leaf
+//   sk:tree/_classes.py:1026-1061    a tree's proba = the leaf's stored class fractions
+//   sk:ensemble/_forest.py:704-716,952-962  out(f64) += proba, tree by tree in estimator order; /= n_trees
+//   sk:ensemble/_forest.py:906       argmax, first maximum
+//
+// Data layout.  Every tree is re-laid in preorder so that the left child is always the next node; a
+// node is 8 bytes:  x = threshold as float32, rounded DOWN from sklearn's float64 threshold
+// (for a float32 feature value v:  (double)v <= t  <=>  v <= floor32(t), so the compare is bit-exact
+// in fp32);  y = feature (8 bits) | distance to the right child << 8.  Leaves set y's top bit; a pure
+// leaf (one class fraction == 1.0) carries its class in y, an impure leaf indexes a table of fp64
+// fraction vectors kept in HBM.  Trees are packed, in estimator order, into groups that fit the shared
+// memory tree buffer.
+//
+// Kernel.  A CTA owns a tile of 1024 rows: the tile is staged transposed in shared memory
+// (xs[f][row]: every lane reads its own bank whatever feature its node tests), per-row fp64
+// class accumulators live in shared memory next to it, and each group of trees is streamed from L2
+// into the tree buffer once per tile.  A thread walks its two rows through the group's trees one
+// tree after another without re-converging with its neighbours (a lane that reaches a leaf starts
+// the next tree at once), adding each tree's fractions to its accumulators in tree order -- the
+// same fp64 addition sequence as sklearn's `out += proba`, hence identical bits.
+// Trees larger than the buffer are walked in place in HBM/L2.
+// Algorithmic bytes per row: 4*d in + 4 out (+ 8 per node visit).
+#include <cmath>
+#include <vector>
+
+#include "common.h"
+
+namespace tcsdn {
+
+constexpr int kFThreads = 512;
+constexpr int kRPT = 2;                       // rows per thread
+constexpr int kFRows = kFThreads * kRPT;      // rows per tile
+constexpr uint32_t kLeaf = 0x80000000u;
+constexpr uint32_t kPure = 0x40000000u;
+
+struct ForestArgs {
+    const uint2 *nodes;
+    const int32_t *tree_base;    // [n_trees+1]
+    const int32_t *group_begin;  // [n_groups+1]
+    const double *leaf_val;
+    int n_trees, n_groups, d, C;
+    int node_cap;                // nodes in the smem tree buffer
+    int64_t n;
+};
+
+template <bool IN_SMEM>
+__device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, int node0, const int32_t *tb, int t_begin,
+                                           int t_end, const float *xs, double *acc, const double *leaf_val, int C,
+                                           int r0, int nrows_live) {
+    int t[kRPT], base[kRPT], idx[kRPT];
+    bool act[kRPT];
+#pragma unroll
+    for (int q = 0; q < kRPT; ++q) {
+        t[q] = t_begin;
+        base[q] = tb[t_begin] - node0;
+        idx[q] = 0;
+        act[q] = (r0 + q * kFThreads) < nrows_live;
+    }
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kRPT; ++q) any |= act[q];
+    while (any) {
+        uint2 nd[kRPT];
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q)
+            if (act[q]) nd[q] = np[base[q] + idx[q]];
+        any = false;
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) {
+            if (!act[q]) continue;
+            const int r = r0 + q * kFThreads;
+            if (nd[q].y & kLeaf) {
+                if (nd[q].y & kPure) {
+                    double *a = acc + (nd[q].y & 0xFFu) * kFRows + r;
+                    *a = *a + 1.0;
+                } else {
+                    const double *lv = leaf_val + (size_t)nd[q].x * C;
+                    for (int c = 0; c < C; ++c) {
+                        double v = lv[c];
+                        if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
+                    }
+                }
+                ++t[q];
+                if (t[q] == t_end) {
+                    act[q] = false;
+                } else {
+                    base[q] = tb[t[q]] - node0;
+                    idx[q] = 0;
+                }
+            } else {
+                float x = xs[(nd[q].y & 0xFFu) * kFRows + r];
+                idx[q] += (x <= __uint_as_float(nd[q].x)) ? 1 : (int)(nd[q].y >> 8);
+            }
+            any |= act[q];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_constant__ ForestArgs A,
+                                                              const T *__restrict__ X,
+                                                              int32_t *__restrict__ labels,
+                                                              double *__restrict__ proba, int32_t *flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = A.d, C = A.C;
+    float *xs = reinterpret_cast<float *>(smem_raw);                       // [d][kFRows]
+    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)d * kFRows * 4);  // [C][kFRows]
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + (size_t)d * kFRows * 4 + (size_t)C * kFRows * 8);
+    __shared__ int32_t s_tb[1];  // placeholder to keep static smem non-empty (tree_base is read from L1)
+
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (A.n + kFRows - 1) / kFRows;
+    const bool single = (A.n_groups == 1) && (A.tree_base[A.n_trees] <= A.node_cap);
+    if (single) {
+        const int nn = A.tree_base[A.n_trees];
+        for (int i = tid; i < nn; i += kFThreads) snodes[i] = A.nodes[i];
+    }
+    float nf = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kFRows;
+        const int live = (int)((A.n - row0) < kFRows ? (A.n - row0) : kFRows);
+        __syncthreads();  // previous tile fully consumed
+        // stage the tile transposed, casting to float32 exactly like np.asarray(X, dtype=float32)
+        {
+            const T *src = X + row0 * d;
+            const int total = live * d;
+            int r = tid / d, f = tid - r * d;          // element tid
+            const int dr = kFThreads / d, df = kFThreads - dr * d;
+            for (int e = tid; e < total; e += kFThreads) {
+                float v = static_cast<float>(src[e]);
+                nf = fmaf(v, 0.f, nf);
+                xs[f * kFRows + r] = v;
+                r += dr; f += df;
+                if (f >= d) { f -= d; r += 1; }
+            }
+            for (int i = tid; i < C * kFRows; i += kFThreads) acc[i] = 0.0;
+        }
+        for (int g = 0; g < A.n_groups; ++g) {
+            const int t_begin = A.group_begin[g], t_end = A.group_begin[g + 1];
+            const int node0 = A.tree_base[t_begin];
+            const int gn = A.tree_base[t_end] - node0;
+            const bool in_smem = gn <= A.node_cap;
+            if (!single && in_smem) {
+                __syncthreads();  // everyone is done with the previous group's nodes
+                for (int i = tid; i < gn; i += kFThreads) snodes[i] = A.nodes[node0 + i];
+            }
+            __syncthreads();
+            if (in_smem)
+                walk_group<true>(snodes, node0, A.tree_base, t_begin, t_end, xs, acc, A.leaf_val, C, tid, live);
+            else
+                walk_group<false>(A.nodes + node0, node0, A.tree_base, t_begin, t_end, xs, acc, A.leaf_val, C,
+                                  tid, live);
+        }
+        // each thread finalises its own rows (only it touched their accumulators)
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) {
+            const int r = tid + q * kFThreads;
+            if (r >= live) continue;
+            int arg = 0;
+            double best = 0.0;
+            const double nt = (double)A.n_trees;
+            for (int c = 0; c < C; ++c) {
+                double p = acc[c * kFRows + r] / nt;
+                if (proba) proba[(row0 + r) * C + c] = p;
+                if (c == 0 || p > best) { best = p; arg = c; }
+            }
+            labels[row0 + r] = arg;
+        }
+    }
+    if (flag && nf != nf) atomicOr(flag, 1);
+    (void)s_tb;
+}
+
+static float floor32(double t) {
+    float f = static_cast<float>(t);
+    if (static_cast<double>(f) > t) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left, const int32_t *right,
+                const int32_t *feature, const double *threshold, const double *value, int n_trees, int C) {
+    const int d = m->d;
+    if (d > 255 || C > 255) { set_error("forest: d and n_classes must be <= 255"); return TCSDN_EINVAL; }
+    int dev_smem = 0;
+    TCSDN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->dev));
+    const int64_t fixed = (int64_t)d * kFRows * 4 + (int64_t)C * kFRows * 8 + 1024;
+    if (fixed + 8 * 64 > dev_smem) {
+        set_error("forest: d=%d, n_classes=%d need %lld bytes of shared memory per tile (device has %d)", d, C,
+                  (long long)fixed, dev_smem);
+        return TCSDN_EINVAL;
+    }
+    m->group_node_cap = (int)((dev_smem - fixed) / 8);
+
+    std::vector<uint2> nodes;
+    std::vector<int32_t> tree_base(1, 0), group_begin(1, 0);
+    std::vector<double> leaf_val;
+    nodes.reserve((size_t)tree_offsets[n_trees]);
+    std::vector<int32_t> stack, newidx;
+    int64_t group_nodes = 0;
+    for (int t = 0; t < n_trees; ++t) {
+        const int64_t o = tree_offsets[t];
+        const int64_t nn = tree_offsets[t + 1] - o;
+        if (nn <= 0) { set_error("forest: tree %d is empty", t); return TCSDN_EINVAL; }
+        const size_t out0 = nodes.size();
+        // preorder relabel: iterative DFS, left before right
+        newidx.assign((size_t)nn, -1);
+        std::vector<int32_t> order;
+        order.reserve((size_t)nn);
+        stack.clear();
+        stack.push_back(0);
+        while (!stack.empty()) {
+            int32_t u = stack.back();
+            stack.pop_back();
+            if (u < 0 || u >= nn || newidx[u] != -1) { set_error("forest: tree %d is not a tree", t); return TCSDN_EINVAL; }
+            newidx[u] = (int32_t)order.size();
+            order.push_back(u);
+            if (left[o + u] != -1) {
+                stack.push_back(right[o + u]);
+                stack.push_back(left[o + u]);
+            }
+        }
+        nodes.resize(out0 + order.size());
+        for (size_t i = 0; i < order.size(); ++i) {
+            const int32_t u = order[i];
+            uint2 nd;
+            if (left[o + u] == -1) {
+                const double *v = value + (o + u) * C;
+                int ones = 0, zeros = 0, cls = 0;
+                for (int c = 0; c < C; ++c) {
+                    if (v[c] == 1.0) { ones++; cls = c; }
+                    else if (v[c] == 0.0) zeros++;
+                }
+                if (ones == 1 && zeros == C - 1) {
+                    nd.x = 0;
+                    nd.y = kLeaf | kPure | (uint32_t)cls;
+                } else {
+                    nd.x = (uint32_t)(leaf_val.size() / C);
+                    nd.y = kLeaf;
+                    leaf_val.insert(leaf_val.end(), v, v + C);
+                }
+            } else {
+                const int32_t f = feature[o + u];
+                if (f < 0 || f >= d) { set_error("forest: feature index %d out of range", f); return TCSDN_EINVAL; }
+                const int64_t rel = (int64_t)newidx[right[o + u]] - (int64_t)i;
+                if (newidx[left[o + u]] != (int32_t)i + 1 || rel < 2 || rel >= (1 << 23)) {
+                    set_error("forest: tree %d too deep/large to encode", t);
+                    return TCSDN_EINVAL;
+                }
+                float th = floor32(threshold[o + u]);
+                memcpy(&nd.x, &th, 4);
+                nd.y = (uint32_t)f | ((uint32_t)rel << 8);
+            }
+            nodes[out0 + i] = nd;
+        }
+        const int64_t tn = (int64_t)order.size();
+        // groups: consecutive trees whose nodes fit the buffer together; an oversize tree stands alone
+        // (group_nodes > cap marks "the open group is an oversize tree")
+        if (t == 0) {
+            group_nodes = tn;
+        } else if (tn > m->group_node_cap || group_nodes > m->group_node_cap ||
+                   group_nodes + tn > m->group_node_cap) {
+            group_begin.push_back(t);
+            group_nodes = tn;
+        } else {
+            group_nodes += tn;
+        }
+        if (group_nodes <= m->group_node_cap && group_nodes > m->max_group_nodes)
+            m->max_group_nodes = (int)group_nodes;
+        if (nodes.size() > (size_t)INT32_MAX) { set_error("forest: more than 2^31 nodes"); return TCSDN_EINVAL; }
+        tree_base.push_back((int32_t)nodes.size());
+    }
+    group_begin.push_back(n_trees);
+    m->n_trees = n_trees;
+    m->n_groups = (int)group_begin.size() - 1;
+    m->n_nodes = (int64_t)nodes.size();
+    if (leaf_val.empty()) leaf_val.assign((size_t)C, 0.0);
+    TCSDN_TRY(upload(&m->d_nodes, nodes.data(), nodes.size()));
+    TCSDN_TRY(upload(&m->d_tree_base, tree_base.data(), tree_base.size()));
+    TCSDN_TRY(upload(&m->d_group_begin, group_begin.data(), group_begin.size()));
+    TCSDN_TRY(upload(&m->d_leaf_val, leaf_val.data(), leaf_val.size()));
+    return TCSDN_OK;
+}
+
+template <typename T>
+static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+    auto kern = forest_kernel<T>;
+    const int64_t fixed = (int64_t)m->d * kFRows * 4 + (int64_t)m->n_classes * kFRows * 8;
+    int64_t buf_nodes = m->n_groups == 1 && m->n_nodes <= m->group_node_cap ? m->n_nodes : m->group_node_cap;
+    if (m->max_group_nodes > 0 && m->n_groups > 1) buf_nodes = m->max_group_nodes;
+    if (buf_nodes < 64) buf_nodes = 64;
+    const size_t smem = (size_t)fixed + (size_t)buf_nodes * 8;
+    TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ForestArgs A;
+    A.nodes = m->d_nodes; A.tree_base = m->d_tree_base; A.group_begin = m->d_group_begin;
+    A.leaf_val = m->d_leaf_val; A.n_trees = m->n_trees; A.n_groups = m->n_groups; A.d = m->d;
+    A.C = m->n_classes; A.node_cap = (int)buf_nodes; A.n = n;
+    int64_t tiles = (n + kFRows - 1) / kFRows;
+    int64_t grid = tiles < m->sm_count ? tiles : m->sm_count;
+    kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, m->opt_check_finite ? m->d_flag : nullptr);
+    TCSDN_CUDA(cudaGetLastError());
+    return TCSDN_OK;
+}
+
+int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                  cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    m->stats[0] += 1;
+    if (dtype == TCSDN_F32) return launch_forest_t<float>(m, static_cast<const float *>(x), n, labels, scores, st);
+    return launch_forest_t<double>(m, static_cast<const double *>(x), n, labels, scores, st);
+}
+
+}  // namespace tcsdn

@@ -1,0 +1,278 @@
+// scorers.cu -- streaming scorers: LogisticRegression, GaussianNB, KMeans  (SURVEY 8a rows a1-a3).
+//
+// One flow row is 32-96 bytes and is touched once, the model is a few hundred doubles: these three
+// estimators are HBM-bound streams.  Layout: rows stay row-major in HBM exactly as the caller has
+// them; a persistent CTA pulls 256-row tiles into a 4-deep shared-memory ring with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), each thread lifts one row out of
+// shared memory with conflict-free 128-bit loads, scores it in fp64 against parameters that sit in
+// the constant bank (kernel parameters, __grid_constant__) and writes one int32 label.
+// Algorithmic bytes per row: d*sizeof(T) in + 4 out.
+//
+//   linear : sk:linear_model/_base.py:391 (X @ coef_.T + intercept_), :418 argmax / :416 (score > 0)
+//   gnb    : sk:naive_bayes.py:533-545 (_joint_log_likelihood), :114 argmax
+//   kmeans : sk:cluster/_k_means_lloyd.pyx:191-213 (||c||^2 - 2 x.c, strict '<' argmin)
+// Scores are evaluated in fp64 with j ascending; they differ from numpy/BLAS only in association
+// (<= 1e-12 relative, tests/test_parity_gpu.py); labels are first-max / first-min like sklearn.
+#include <cfloat>
+
+#include "common.h"
+
+namespace tcsdn {
+
+constexpr int kTile = 256;    // rows per tile == threads per CTA
+constexpr int kStages = 4;
+
+enum : int { KIND_AFFINE_MAX = 0, KIND_AFFINE_MIN = 1, KIND_GNB = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void load_row_smem(const T *tile, int r, double (&x)[D], float &nf) {
+    // 16-byte shared loads; a row is D*sizeof(T) bytes, a multiple of 16 for every instantiated D
+    constexpr int kVec = 16 / sizeof(T);
+    const T *row = tile + r * D;
+#pragma unroll
+    for (int v = 0; v < D / kVec; ++v) {
+        if constexpr (sizeof(T) == 4) {
+            float4 q = *reinterpret_cast<const float4 *>(row + v * 4);
+            x[v * 4 + 0] = q.x; x[v * 4 + 1] = q.y; x[v * 4 + 2] = q.z; x[v * 4 + 3] = q.w;
+            nf = fmaf(q.x, 0.f, nf); nf = fmaf(q.y, 0.f, nf); nf = fmaf(q.z, 0.f, nf); nf = fmaf(q.w, 0.f, nf);
+        } else {
+            double2 q = *reinterpret_cast<const double2 *>(row + v * 2);
+            x[v * 2 + 0] = q.x; x[v * 2 + 1] = q.y;
+            nf += static_cast<float>(q.x * 0.0);  // 0 for finite values, NaN for inf/NaN
+            nf += static_cast<float>(q.y * 0.0);
+        }
+    }
+}
+
+template <int D, int R, int KIND>
+__device__ __forceinline__ int score_row(const ScorerParams &P, const double (&x)[D], double (&s)[R]) {
+    int arg = 0;
+    double best = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double acc = P.c[r];
+        if constexpr (KIND == KIND_GNB) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                double df = x[j] - P.a[r * D + j];
+                acc = fma(df * df, P.b[r * D + j], acc);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc = fma(x[j], P.a[r * D + j], acc);
+        }
+        s[r] = acc;
+        bool better = (KIND == KIND_AFFINE_MIN) ? (acc < best) : (acc > best);
+        if (r == 0 || better) { best = acc; arg = r; }
+    }
+    if (R == 1 && KIND == KIND_AFFINE_MAX) arg = s[0] > 0.0 ? 1 : 0;
+    return arg;
+}
+
+template <typename T, int D, int R, int KIND>
+__global__ void __launch_bounds__(kTile) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
+                                                             const T *__restrict__ X, int64_t n,
+                                                             int32_t *__restrict__ labels,
+                                                             double *__restrict__ scores, int32_t *flag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
+    T *tiles = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTileBytes);
+
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int64_t first = blockIdx.x;
+    const int64_t stride = gridDim.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t tile, int stage) {
+        int64_t row0 = tile * kTile;
+        int64_t rows = n - row0 < kTile ? n - row0 : kTile;
+        uint32_t bytes = static_cast<uint32_t>(rows) * D * sizeof(T);
+        mbar_expect_tx(&full[stage], bytes);
+        bulk_g2s(reinterpret_cast<unsigned char *>(tiles) + (size_t)stage * kTileBytes, X + row0 * D, bytes,
+                 &full[stage]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            int64_t t = first + (int64_t)s * stride;
+            if (t < n_tiles) issue(t, s);
+        }
+    }
+
+    float nf = 0.f;
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+        const int stage = it % kStages;
+        const uint32_t parity = (it / kStages) & 1;
+        mbar_wait(&full[stage], parity);
+        const int64_t row = tile * kTile + tid;
+        const bool live = row < n;
+        double x[D];
+        if (live) {
+            load_row_smem<T, D>(reinterpret_cast<const T *>(reinterpret_cast<unsigned char *>(tiles) +
+                                                            (size_t)stage * kTileBytes),
+                                tid, x, nf);
+        }
+        __syncthreads();  // every thread has lifted its row: the stage may be refilled
+        if (tid == 0) {
+            int64_t nt = tile + (int64_t)kStages * stride;
+            if (nt < n_tiles) issue(nt, stage);
+        }
+        if (live) {
+            double s[R];
+            int arg = score_row<D, R, KIND>(P, x, s);
+            labels[row] = arg;
+            if (scores) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) scores[row * R + r] = s[r];
+            }
+        }
+    }
+    if (flag && nf != nf) atomicOr(flag, 1);
+}
+
+// Generic path: any d, any number of score rows, unaligned X; parameters from HBM through L1.
+template <typename T>
+__global__ void __launch_bounds__(256) scorer_generic_kernel(const T *__restrict__ X, int64_t n, int d, int R,
+                                                             int kind, const double *__restrict__ A,
+                                                             const double *__restrict__ B,
+                                                             const double *__restrict__ Cc,
+                                                             int32_t *__restrict__ labels,
+                                                             double *__restrict__ scores, int32_t *flag) {
+    float nf = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n;
+         row += (int64_t)gridDim.x * blockDim.x) {
+        const T *x = X + row * d;
+        int arg = 0;
+        double best = 0.0;
+        for (int r = 0; r < R; ++r) {
+            double acc = Cc[r];
+            if (kind == KIND_GNB) {
+                for (int j = 0; j < d; ++j) {
+                    double df = static_cast<double>(x[j]) - A[(int64_t)r * d + j];
+                    acc = fma(df * df, B[(int64_t)r * d + j], acc);
+                }
+            } else {
+                for (int j = 0; j < d; ++j) acc = fma(static_cast<double>(x[j]), A[(int64_t)r * d + j], acc);
+            }
+            if (scores) scores[row * R + r] = acc;
+            bool better = (kind == KIND_AFFINE_MIN) ? (acc < best) : (acc > best);
+            if (r == 0 || better) { best = acc; arg = r; }
+        }
+        if (R == 1 && kind == KIND_AFFINE_MAX) arg = best > 0.0 ? 1 : 0;
+        for (int j = 0; j < d; ++j) nf += static_cast<float>(x[j] * static_cast<T>(0));
+        labels[row] = arg;
+    }
+    if (flag && nf != nf) atomicOr(flag, 1);
+}
+
+template <typename T, int D, int R, int KIND>
+static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                        cudaStream_t st) {
+    auto kern = scorer_tiled_kernel<T, D, R, KIND>;
+    const size_t smem = (size_t)kStages * kTile * D * sizeof(T) + kStages * sizeof(uint64_t);
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t n_tiles = (n + kTile - 1) / kTile;
+    int ctas_per_sm = sizeof(T) == 4 ? 4 : 2;
+    int64_t grid = (int64_t)m->sm_count * ctas_per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, kTile, smem, st>>>(m->sp, x, n, labels, scores, flag);
+    TCSDN_CUDA(cudaGetLastError());
+    return TCSDN_OK;
+}
+
+template <typename T, int D, int KIND>
+static int dispatch_rows(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                         cudaStream_t st) {
+    switch (m->n_classes) {
+#define TCSDN_CASE(RR) \
+    case RR: return launch_tiled<T, D, RR, KIND>(m, x, n, labels, scores, flag, st);
+        TCSDN_CASE(1) TCSDN_CASE(2) TCSDN_CASE(3) TCSDN_CASE(4) TCSDN_CASE(5) TCSDN_CASE(6) TCSDN_CASE(7)
+        TCSDN_CASE(8)
+#undef TCSDN_CASE
+    }
+    return TCSDN_EINVAL;
+}
+
+template <typename T, int D>
+static int dispatch_kind(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
+                         int32_t *flag, cudaStream_t st) {
+    if (kind == KIND_GNB) return dispatch_rows<T, D, KIND_GNB>(m, x, n, labels, scores, flag, st);
+    if (kind == KIND_AFFINE_MIN) return dispatch_rows<T, D, KIND_AFFINE_MIN>(m, x, n, labels, scores, flag, st);
+    return dispatch_rows<T, D, KIND_AFFINE_MAX>(m, x, n, labels, scores, flag, st);
+}
+
+template <typename T>
+static int launch_scorer_t(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
+                           int32_t *flag, cudaStream_t st) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (m->sp_valid && aligned && m->opt_engine != 1) {
+        if (m->d == 12) return dispatch_kind<T, 12>(m, kind, x, n, labels, scores, flag, st);
+        if (m->d == 8) return dispatch_kind<T, 8>(m, kind, x, n, labels, scores, flag, st);
+        if (m->d == 16) return dispatch_kind<T, 16>(m, kind, x, n, labels, scores, flag, st);
+        if (m->d == 4) return dispatch_kind<T, 4>(m, kind, x, n, labels, scores, flag, st);
+    }
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)m->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    scorer_generic_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(x, n, m->d, m->n_classes, kind, m->d_a, m->d_b,
+                                                               m->d_c, labels, scores, flag);
+    TCSDN_CUDA(cudaGetLastError());
+    return TCSDN_OK;
+}
+
+int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                  cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    int kind = m->kind == TCSDN_KIND_GNB ? KIND_GNB : (m->kind == TCSDN_KIND_KMEANS ? KIND_AFFINE_MIN : KIND_AFFINE_MAX);
+    int32_t *flag = m->opt_check_finite ? m->d_flag : nullptr;
+    m->stats[0] += 1;
+    if (dtype == TCSDN_F32) return launch_scorer_t<float>(m, kind, static_cast<const float *>(x), n, labels, scores, flag, st);
+    return launch_scorer_t<double>(m, kind, static_cast<const double *>(x), n, labels, scores, flag, st);
+}
+
+}  // namespace tcsdn
