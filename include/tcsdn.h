@@ -119,8 +119,8 @@ int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
 int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t x_dtype,
                   int32_t x_loc, int32_t *labels_out, double *scores_out, void *cuda_stream);
 
-/* After device-pointer predicts: synchronise `cuda_stream` and report TCSDN_ENONFINITE if any of them saw
- * NaN/inf rows (host-pointer predicts do this themselves). */
+/* After device-pointer predicts: synchronise `cuda_stream` and report TCSDN_ENONFINITE if any predict since the
+ * last check saw NaN/inf rows (the flag is sticky and cleared here; host-pointer predicts check themselves). */
 int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream);
 
 /* SVC.decision_function(decision_function_shape='ovr'): votes + conf/(3(|conf|+1)) from the OvO values

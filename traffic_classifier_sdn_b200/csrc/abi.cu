@@ -56,6 +56,8 @@ static bool finite_all(const double *p, size_t n) {
 static void free_workspace(Workspace *w) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(w->x[i].p); cudaFree(w->labels[i].p); cudaFree(w->scores[i].p);
+        if (w->h_labels[i]) cudaFreeHost(w->h_labels[i]);
+        if (w->h_scores[i]) cudaFreeHost(w->h_scores[i]);
         if (w->stream[i]) cudaStreamDestroy(w->stream[i]);
         if (w->done[i]) cudaEventDestroy(w->done[i]);
     }
@@ -70,6 +72,16 @@ static int ensure(DeviceBuf &b, size_t bytes) {
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return TCSDN_ENOMEM; }
     b.bytes = bytes;
+    return TCSDN_OK;
+}
+
+static int ensure_pinned(void **p, size_t *have, size_t bytes) {
+    if (*have >= bytes) return TCSDN_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return TCSDN_ENOMEM; }
+    *have = bytes;
     return TCSDN_OK;
 }
 
@@ -188,12 +200,14 @@ int tcsdn_gnb_create(const double *theta, const double *var, const double *class
     tcsdn_model *m;
     TCSDN_TRY(model_base(&m, TCSDN_KIND_GNB, d, n_classes, n_classes));
     // jll_i = log(prior_i) - 0.5 sum_j log(2 pi var_ij) - 0.5 sum_j (x_j - theta_ij)^2 / var_ij  (sk:naive_bayes.py:537-542)
-    std::vector<double> a(theta, theta + (size_t)n_classes * d), b((size_t)n_classes * d), c(n_classes);
+    // device form: jll_i = c_i - sum_j (a_ij x_j - b_ij)^2 with a = 1/sqrt(2 var), b = theta * a
+    std::vector<double> a((size_t)n_classes * d), b((size_t)n_classes * d), c(n_classes);
     for (int i = 0; i < n_classes; ++i) {
         double s = 0.0;
         for (int j = 0; j < d; ++j) {
             s += std::log(2.0 * M_PI * var[(size_t)i * d + j]);
-            b[(size_t)i * d + j] = -0.5 / var[(size_t)i * d + j];
+            a[(size_t)i * d + j] = 1.0 / std::sqrt(2.0 * var[(size_t)i * d + j]);
+            b[(size_t)i * d + j] = theta[(size_t)i * d + j] * a[(size_t)i * d + j];
         }
         c[i] = std::log(class_prior[i]) + (-0.5 * s);
     }
@@ -352,24 +366,40 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
     for (int i = 0; i < 8; ++i) m->stats[i] = 0;
 
     if (x_loc == TCSDN_DEVICE) {
-        cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-        if (m->opt_check_finite) TCSDN_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int32_t), st));
-        return run_device(m, x, n, x_dtype, labels_out, scores_out, st);
+        // the non-finite flag is sticky on this path: kernels only OR into it, tcsdn_sync_check reads and clears it
+        // (no memset node per predict: a 1M-row predict lasts microseconds)
+        return run_device(m, x, n, x_dtype, labels_out, scores_out, static_cast<cudaStream_t>(cuda_stream));
     }
 
-    // host pointers: double-buffered H2D -> kernel -> D2H over two internal streams
+    // host pointers: chunks alternate between two internal streams, so the H2D copy of chunk c+1 runs under the
+    // kernels of chunk c and the D2H of chunk c-1 (PCIe is full duplex).  Results land in pinned staging
+    // buffers (a D2H copy into pageable memory would block this thread and serialise the pipeline) and are
+    // memcpy'd to the caller's arrays when their slot is recycled.
     const size_t esz = x_dtype == TCSDN_F32 ? 4 : 8;
     const size_t row_bytes = (size_t)d * esz;
     int64_t chunk = m->opt_chunk_rows;
     if (chunk <= 0) {
-        chunk = (int64_t)((64u << 20) / row_bytes);   // ~64 MiB of rows per chunk
+        chunk = (int64_t)((16u << 20) / row_bytes);   // ~16 MiB of rows per chunk
         chunk = (chunk / 1024) * 1024;
         if (chunk < 1024) chunk = 1024;
     }
     if (chunk > n) chunk = n;
+    const size_t sc_cols = scores_out ? (size_t)m->score_cols : 0;
     Workspace *w = nullptr;
     TCSDN_TRY(acquire_workspace(m, &w));
     int rc = TCSDN_OK;
+    int64_t pend_off[2] = {-1, -1}, pend_rows[2] = {0, 0};
+    auto drain = [&](int slot) -> int {   // wait for the slot's last chunk and hand its results to the caller
+        if (pend_off[slot] < 0) return TCSDN_OK;
+        cudaError_t e = cudaEventSynchronize(w->done[slot]);
+        if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
+        memcpy(labels_out + pend_off[slot], w->h_labels[slot], (size_t)pend_rows[slot] * sizeof(int32_t));
+        if (sc_cols)
+            memcpy(scores_out + (size_t)pend_off[slot] * sc_cols, w->h_scores[slot],
+                   (size_t)pend_rows[slot] * sc_cols * sizeof(double));
+        pend_off[slot] = -1;
+        return TCSDN_OK;
+    };
     do {
         if (m->opt_check_finite) {
             cudaError_t e = cudaMemsetAsync(m->d_flag, 0, sizeof(int32_t), w->stream[0]);
@@ -382,23 +412,33 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
         while (done < n && rc == TCSDN_OK) {
             const int64_t rows = (n - done) < chunk ? (n - done) : chunk;
             cudaStream_t st = w->stream[slot];
+            if ((rc = drain(slot)) != TCSDN_OK) break;
             if ((rc = ensure(w->x[slot], (size_t)chunk * row_bytes)) != TCSDN_OK) break;
             if ((rc = ensure(w->labels[slot], (size_t)chunk * sizeof(int32_t))) != TCSDN_OK) break;
-            if (scores_out && (rc = ensure(w->scores[slot], (size_t)chunk * m->score_cols * sizeof(double))) != TCSDN_OK) break;
+            if ((rc = ensure_pinned(&w->h_labels[slot], &w->h_labels_bytes[slot], (size_t)chunk * sizeof(int32_t))) != TCSDN_OK) break;
+            if (sc_cols) {
+                if ((rc = ensure(w->scores[slot], (size_t)chunk * sc_cols * sizeof(double))) != TCSDN_OK) break;
+                if ((rc = ensure_pinned(&w->h_scores[slot], &w->h_scores_bytes[slot], (size_t)chunk * sc_cols * sizeof(double))) != TCSDN_OK) break;
+            }
             cudaError_t e = cudaMemcpyAsync(w->x[slot].p, static_cast<const char *>(x) + (size_t)done * row_bytes,
                                             (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; break; }
             rc = run_device(m, w->x[slot].p, rows, x_dtype, static_cast<int32_t *>(w->labels[slot].p),
-                            scores_out ? static_cast<double *>(w->scores[slot].p) : nullptr, st);
+                            sc_cols ? static_cast<double *>(w->scores[slot].p) : nullptr, st);
             if (rc != TCSDN_OK) break;
-            e = cudaMemcpyAsync(labels_out + done, w->labels[slot].p, (size_t)rows * sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && scores_out)
-                e = cudaMemcpyAsync(scores_out + (size_t)done * m->score_cols, w->scores[slot].p,
-                                    (size_t)rows * m->score_cols * sizeof(double), cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(w->h_labels[slot], w->labels[slot].p, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && sc_cols)
+                e = cudaMemcpyAsync(w->h_scores[slot], w->scores[slot].p, (size_t)rows * sc_cols * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(w->done[slot], st);
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; break; }
+            pend_off[slot] = done; pend_rows[slot] = rows;
             done += rows;
             slot ^= 1;
+        }
+        for (int i = 0; i < 2; ++i) {   // oldest first
+            int r2 = drain(slot ^ i ^ 0);
+            if (rc == TCSDN_OK) rc = r2;
         }
         for (int i = 0; i < 2; ++i) {
             cudaError_t e = cudaStreamSynchronize(w->stream[i]);
@@ -407,7 +447,11 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
         if (rc == TCSDN_OK && m->opt_check_finite) {
             cudaError_t e = cudaMemcpy(w->h_flag, m->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { set_error("flag read failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; }
-            else if (*w->h_flag) { set_error("Input X contains NaN or infinity"); rc = TCSDN_ENONFINITE; }
+            else if (*w->h_flag) {
+                cudaMemset(m->d_flag, 0, sizeof(int32_t));
+                set_error("Input X contains NaN or infinity");
+                rc = TCSDN_ENONFINITE;
+            }
         }
     } while (0);
     release_workspace(m, w);
@@ -420,7 +464,11 @@ int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream) {
     if (!m->opt_check_finite) return TCSDN_OK;
     int32_t f = 0;
     TCSDN_CUDA(cudaMemcpy(&f, m->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (f) { set_error("Input X contains NaN or infinity"); return TCSDN_ENONFINITE; }
+    if (f) {
+        TCSDN_CUDA(cudaMemset(m->d_flag, 0, sizeof(int32_t)));
+        set_error("Input X contains NaN or infinity");
+        return TCSDN_ENONFINITE;
+    }
     return TCSDN_OK;
 }
 

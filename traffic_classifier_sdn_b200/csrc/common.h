@@ -38,7 +38,7 @@ constexpr int kMaxClasses = 64;
 // kernels read them as constant-bank operands.  a/b are [rows][d] (row stride d), c is [rows].
 //   linear : s_r = c_r + sum_j a_rj x_j                         (a = coef, c = intercept), argmax
 //   kmeans : s_r = c_r + sum_j a_rj x_j                         (a = -2 centers, c = ||c||^2), argmin
-//   gnb    : s_r = c_r + sum_j b_rj (x_j - a_rj)^2              (a = theta, b = -0.5/var), argmax
+//   gnb    : s_r = c_r - sum_j (a_rj x_j - b_rj)^2              (a = 1/sqrt(2 var), b = theta * a), argmax
 struct ScorerParams {
     double a[kMaxClassesFast * 16];
     double b[kMaxClassesFast * 16];
@@ -52,6 +52,9 @@ struct DeviceBuf {
 
 struct Workspace {  // per-call scratch for the host-pointer pipeline
     DeviceBuf x[2], labels[2], scores[2];
+    void *h_labels[2] = {nullptr, nullptr};   // pinned D2H staging (results are memcpy'd to the caller's buffer)
+    void *h_scores[2] = {nullptr, nullptr};
+    size_t h_labels_bytes[2] = {0, 0}, h_scores_bytes[2] = {0, 0};
     cudaStream_t stream[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     int32_t *h_flag = nullptr;  // pinned

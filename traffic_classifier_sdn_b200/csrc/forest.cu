@@ -9,9 +9,9 @@
 // Data layout.  Every tree is re-laid in preorder so that the left child is always the next node; a
 // node is 8 bytes:  x = threshold as float32, rounded DOWN from sklearn's float64 threshold
 // (for a float32 feature value v:  (double)v <= t  <=>  v <= floor32(t), so the compare is bit-exact
-// in fp32);  y = feature (8 bits) | distance to the right child << 8.  Leaves set y's top bit; a pure
-// leaf (one class fraction == 1.0) carries its class in y, an impure leaf indexes a table of fp64
-// fraction vectors kept in HBM.  Trees are packed, in estimator order, into groups that fit the shared
+// in fp32);  y = feature << 24 | distance to the right child.  Leaves set y's top bit and keep in x the
+// position of the next tree's root; a pure leaf (one class fraction == 1.0) carries its class in y, an
+// impure leaf indexes a table of fp64 fraction vectors kept in HBM (see walk_group for the bit layout).  Trees are packed, in estimator order, into groups that fit the shared
 // memory tree buffer.
 //
 // Kernel.  A CTA owns a tile of 1024 rows: the tile is staged transposed in shared memory
@@ -34,7 +34,8 @@ constexpr int kFThreads = 512;
 constexpr int kRPT = 2;                       // rows per thread
 constexpr int kFRows = kFThreads * kRPT;      // rows per tile
 constexpr uint32_t kLeaf = 0x80000000u;
-constexpr uint32_t kPure = 0x40000000u;
+constexpr uint32_t kPure = 0x00800000u;
+constexpr uint32_t kEnd = 0xFFFFFFFFu;      // 'no next tree' marker in a leaf's x field
 
 struct ForestArgs {
     const uint2 *nodes;
@@ -46,54 +47,64 @@ struct ForestArgs {
     int64_t n;
 };
 
+// One chain = one row walking the trees of a group back to back.  `pos` is the node index relative to the
+// group's first node.
+//   internal node: x = threshold (fp32), y = feature << 24 | distance to the right child (left child = pos + 1)
+//   leaf:          y bit 31 set, bits 30..24 zero (so the "feature" of a leaf reads as 0 and needs no masking),
+//                  bit 23 = pure, low 23 bits = class (pure) or index into the fraction table (impure);
+//                  x = position of the NEXT tree's root, or kEnd after the group's last tree.
+// The body is branch-free for internal nodes and pure leaves: the accumulator read-modify-write is
+// predicated inline PTX, so lanes sitting on a leaf never serialise the warp.  Impure leaves (rare) branch.
+__device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .f64 t;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "@p ld.shared.f64 t, [%0];\n"
+        "@p add.rn.f64 t, t, 0d3FF0000000000000;\n"
+        "@p st.shared.f64 [%0], t;\n"
+        "}\n" ::"r"(smem_addr),
+        "r"((uint32_t)pred)
+        : "memory");
+}
+
 template <bool IN_SMEM>
-__device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, int node0, const int32_t *tb, int t_begin,
-                                           int t_end, const float *xs, double *acc, const double *leaf_val, int C,
-                                           int r0, int nrows_live) {
-    int t[kRPT], base[kRPT], idx[kRPT];
+__device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, const float *xs, double *acc,
+                                           const double *leaf_val, int C, int r0, int nrows_live) {
+    uint32_t pos[kRPT];
     bool act[kRPT];
+    bool any = false;
+    const uint32_t acc_base = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
 #pragma unroll
     for (int q = 0; q < kRPT; ++q) {
-        t[q] = t_begin;
-        base[q] = tb[t_begin] - node0;
-        idx[q] = 0;
+        pos[q] = 0;
         act[q] = (r0 + q * kFThreads) < nrows_live;
+        any |= act[q];
     }
-    bool any = false;
-#pragma unroll
-    for (int q = 0; q < kRPT; ++q) any |= act[q];
     while (any) {
         uint2 nd[kRPT];
 #pragma unroll
-        for (int q = 0; q < kRPT; ++q)
-            if (act[q]) nd[q] = np[base[q] + idx[q]];
+        for (int q = 0; q < kRPT; ++q) nd[q] = np[act[q] ? pos[q] : 0u];
         any = false;
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {
-            if (!act[q]) continue;
-            const int r = r0 + q * kFThreads;
-            if (nd[q].y & kLeaf) {
-                if (nd[q].y & kPure) {
-                    double *a = acc + (nd[q].y & 0xFFu) * kFRows + r;
-                    *a = *a + 1.0;
-                } else {
-                    const double *lv = leaf_val + (size_t)nd[q].x * C;
-                    for (int c = 0; c < C; ++c) {
-                        double v = lv[c];
-                        if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
-                    }
+            const uint32_t r = (uint32_t)(r0 + q * kFThreads);
+            const uint32_t y = nd[q].y;
+            const bool leaf = (int32_t)y < 0;
+            const float x = xs[((y >> 24) & 0x7Fu) * kFRows + r];
+            const uint32_t step = (x <= __uint_as_float(nd[q].x)) ? 1u : (y & 0xFFFFFFu);
+            const bool pure = ((y & (kLeaf | kPure)) == (kLeaf | kPure)) && act[q];
+            acc_add_one_if(acc_base + (((y & 0xFFu) * kFRows + r) << 3), pure);
+            if (leaf && !(y & kPure) && act[q]) {
+                const double *lv = leaf_val + (size_t)(y & 0x7FFFFFu) * C;
+                for (int c = 0; c < C; ++c) {
+                    double v = lv[c];
+                    if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
                 }
-                ++t[q];
-                if (t[q] == t_end) {
-                    act[q] = false;
-                } else {
-                    base[q] = tb[t[q]] - node0;
-                    idx[q] = 0;
-                }
-            } else {
-                float x = xs[(nd[q].y & 0xFFu) * kFRows + r];
-                idx[q] += (x <= __uint_as_float(nd[q].x)) ? 1 : (int)(nd[q].y >> 8);
             }
+            pos[q] = leaf ? nd[q].x : pos[q] + step;
+            act[q] = act[q] && (pos[q] != kEnd);
             any |= act[q];
         }
     }
@@ -149,10 +160,9 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             }
             __syncthreads();
             if (in_smem)
-                walk_group<true>(snodes, node0, A.tree_base, t_begin, t_end, xs, acc, A.leaf_val, C, tid, live);
+                walk_group<true>(snodes, xs, acc, A.leaf_val, C, tid, live);
             else
-                walk_group<false>(A.nodes + node0, node0, A.tree_base, t_begin, t_end, xs, acc, A.leaf_val, C,
-                                  tid, live);
+                walk_group<false>(A.nodes + node0, xs, acc, A.leaf_val, C, tid, live);
         }
         // each thread finalises its own rows (only it touched their accumulators)
 #pragma unroll
@@ -183,7 +193,7 @@ static float floor32(double t) {
 int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left, const int32_t *right,
                 const int32_t *feature, const double *threshold, const double *value, int n_trees, int C) {
     const int d = m->d;
-    if (d > 255 || C > 255) { set_error("forest: d and n_classes must be <= 255"); return TCSDN_EINVAL; }
+    if (d > 127 || C > 255) { set_error("forest: n_features must be <= 127 and n_classes <= 255"); return TCSDN_EINVAL; }
     int dev_smem = 0;
     TCSDN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->dev));
     const int64_t fixed = (int64_t)d * kFRows * 4 + (int64_t)C * kFRows * 8 + 1024;
@@ -233,25 +243,26 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
                     if (v[c] == 1.0) { ones++; cls = c; }
                     else if (v[c] == 0.0) zeros++;
                 }
+                nd.x = 0;  // next-tree root, patched once the groups are known
                 if (ones == 1 && zeros == C - 1) {
-                    nd.x = 0;
                     nd.y = kLeaf | kPure | (uint32_t)cls;
                 } else {
-                    nd.x = (uint32_t)(leaf_val.size() / C);
-                    nd.y = kLeaf;
+                    const size_t li = leaf_val.size() / C;
+                    if (li >= (1u << 23)) { set_error("forest: more than 2^23 impure leaves"); return TCSDN_EINVAL; }
+                    nd.y = kLeaf | (uint32_t)li;
                     leaf_val.insert(leaf_val.end(), v, v + C);
                 }
             } else {
                 const int32_t f = feature[o + u];
                 if (f < 0 || f >= d) { set_error("forest: feature index %d out of range", f); return TCSDN_EINVAL; }
                 const int64_t rel = (int64_t)newidx[right[o + u]] - (int64_t)i;
-                if (newidx[left[o + u]] != (int32_t)i + 1 || rel < 2 || rel >= (1 << 23)) {
-                    set_error("forest: tree %d too deep/large to encode", t);
+                if (newidx[left[o + u]] != (int32_t)i + 1 || rel < 2 || rel >= (1 << 24)) {
+                    set_error("forest: tree %d too large to encode", t);
                     return TCSDN_EINVAL;
                 }
                 float th = floor32(threshold[o + u]);
                 memcpy(&nd.x, &th, 4);
-                nd.y = (uint32_t)f | ((uint32_t)rel << 8);
+                nd.y = ((uint32_t)f << 24) | (uint32_t)rel;
             }
             nodes[out0 + i] = nd;
         }
@@ -273,6 +284,16 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
         tree_base.push_back((int32_t)nodes.size());
     }
     group_begin.push_back(n_trees);
+    // every leaf points at the root of the next tree of its group (position relative to the group's first node)
+    for (size_t g = 0; g + 1 < group_begin.size(); ++g) {
+        const int tb = group_begin[g], te = group_begin[g + 1];
+        const int32_t node0 = tree_base[tb];
+        for (int t = tb; t < te; ++t) {
+            const uint32_t next = (t + 1 < te) ? (uint32_t)(tree_base[t + 1] - node0) : kEnd;
+            for (int32_t i = tree_base[t]; i < tree_base[t + 1]; ++i)
+                if (nodes[i].y & kLeaf) nodes[i].x = next;
+        }
+    }
     m->n_trees = n_trees;
     m->n_groups = (int)group_begin.size() - 1;
     m->n_nodes = (int64_t)nodes.size();

@@ -12,7 +12,14 @@
 //   gnb    : sk:naive_bayes.py:533-545 (_joint_log_likelihood), :114 argmax
 //   kmeans : sk:cluster/_k_means_lloyd.pyx:191-213 (||c||^2 - 2 x.c, strict '<' argmin)
 // Scores are evaluated in fp64 with j ascending; they differ from numpy/BLAS only in association
-// (<= 1e-12 relative, tests/test_parity_gpu.py); labels are first-max / first-min like sklearn.
+// (tests/test_parity_gpu.py); labels are first-max / first-min like sklearn.
+// GaussianNB costs two DFMA per (class, feature) instead of sub, mul, div, add:
+//   t = x * s - theta * s,  s = 1/sqrt(2 var)   (one rounding; theta*s is rounded once on the host)
+//   jll -= t * t
+// The B200 issues 64 DFMA/clk/SM, which makes a 6-class, 8-feature row cost 1.5 clk of fp64 pipe against
+// 1.1 clk of HBM time: the three-operation form was fp64-pipe-bound (ncu r01a: fp64 pipe 62 %, DRAM 22 %).
+// Error: |delta t| <= u |theta s| + u |t|, i.e. the joint log likelihood is exact to ~1e-16 * (theta/sigma)
+// relative to its own terms (<= 1e-11 of the row's largest |jll| in the tests, labels unchanged).
 #include <cfloat>
 
 #include "common.h"
@@ -85,8 +92,8 @@ __device__ __forceinline__ int score_row(const ScorerParams &P, const double (&x
         if constexpr (KIND == KIND_GNB) {
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                double df = x[j] - P.a[r * D + j];
-                acc = fma(df * df, P.b[r * D + j], acc);
+                const double t = fma(x[j], P.a[r * D + j], -P.b[r * D + j]);   // (x - theta) / sqrt(2 var)
+                acc = fma(-t, t, acc);
             }
         } else {
 #pragma unroll
@@ -189,8 +196,8 @@ __global__ void __launch_bounds__(256) scorer_generic_kernel(const T *__restrict
             double acc = Cc[r];
             if (kind == KIND_GNB) {
                 for (int j = 0; j < d; ++j) {
-                    double df = static_cast<double>(x[j]) - A[(int64_t)r * d + j];
-                    acc = fma(df * df, B[(int64_t)r * d + j], acc);
+                    const double t = fma(static_cast<double>(x[j]), A[(int64_t)r * d + j], -B[(int64_t)r * d + j]);
+                    acc = fma(-t, t, acc);
                 }
             } else {
                 for (int j = 0; j < d; ++j) acc = fma(static_cast<double>(x[j]), A[(int64_t)r * d + j], acc);
