@@ -32,7 +32,12 @@ def rel_err(a, b):
 
 @pytest.fixture(scope="module")
 def models(specs):
-    return {k: from_spec(specs[k]) for k in KINDS}
+    """this module pins the fp64 CUDA-core kernels (engine option 1); tests/test_engine_gpu.py covers the
+    tensor-core engine that large KNN / SVC batches take by default"""
+    out = {k: from_spec(specs[k]) for k in KINDS}
+    for k in ("knn", "svc"):
+        out[k].set_option(_lib.OPT_ENGINE, 1)
+    return out
 
 
 # ------------------------------------------------------------------ (a) golden vectors

@@ -116,11 +116,11 @@ static int run_device(tcsdn_model *m, const void *x, int64_t n, int dtype, int32
         case TCSDN_KIND_FOREST: return launch_forest(m, x, n, dtype, labels, scores, st);
         case TCSDN_KIND_KNN:
             if (m->opt_engine != 1 && engine_usable(m, n)) return launch_engine(m, x, n, dtype, labels, scores, st);
-            if (m->opt_engine == 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
+            if (m->opt_engine >= 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
             return launch_knn_exact(m, x, n, dtype, labels, scores, st);
         case TCSDN_KIND_SVC:
             if (m->opt_engine != 1 && engine_usable(m, n)) return launch_engine(m, x, n, dtype, labels, scores, st);
-            if (m->opt_engine == 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
+            if (m->opt_engine >= 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
             return launch_svc_exact(m, x, n, dtype, labels, scores, st);
     }
     set_error("corrupt model handle");
@@ -331,7 +331,7 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
     if (!m) { set_error("model is NULL"); return TCSDN_EINVAL; }
     switch (key) {
         case TCSDN_OPT_ENGINE:
-            if (value < 0 || value > 2) { set_error("engine option must be 0, 1 or 2"); return TCSDN_EINVAL; }
+            if (value < 0 || value > 3) { set_error("engine option must be 0..3"); return TCSDN_EINVAL; }
             m->opt_engine = value; return TCSDN_OK;
         case TCSDN_OPT_CHUNK_ROWS:
             if (value < 0) { set_error("chunk rows must be >= 0"); return TCSDN_EINVAL; }
@@ -345,6 +345,7 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
 int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out) {
     if (!m || !out) { set_error("NULL argument"); return TCSDN_EINVAL; }
     for (int i = 0; i < 8; ++i) out[i] = m->stats[i];
+    if (m->engine) engine_read_stats(m, &out[3], &out[5]);   // cumulative since create(); synchronises the device
     return TCSDN_OK;
 }
 

@@ -135,6 +135,7 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
 int engine_create(tcsdn_model *m);   // builds packed operands for knn / svc handles
 void engine_destroy(tcsdn_model *m);
 bool engine_usable(const tcsdn_model *m, int64_t n);
+void engine_read_stats(const tcsdn_model *m, int64_t *exact_evals, int64_t *maxratio_q40);
 int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
                   cudaStream_t st);
 

@@ -1,15 +1,699 @@
-// dist_engine.cu -- tensor-core (tcgen05) distance engine shared by KNeighbors and SVC.  Placeholder until
-// the engine lands: every handle reports "not usable" and the fp64 CUDA-core kernels run.
+// dist_engine.cu -- tensor-core (tcgen05 / TMEM) distance engine shared by KNeighbors and SVC(rbf).
+//
+// Both estimators need, for every (query row x, reference row t) pair, the squared euclidean distance
+//   d(x,t) = ||x||^2 + ||t||^2 - 2 x.t          (reference rows = training rows / support vectors)
+// KNN  (sk:neighbors/_classification.py:245-312, sk:utils/_heap.pyx:6-88): the k smallest d in heap order;
+// SVC  (sk:svm/src/libsvm/svm.cpp:461-478,2846-2904): K = exp(-gamma d) folded into one-vs-one sums.
+//
+// Numerics.  Features are raw packet/byte counters (up to ~4e5), so a plain bf16 GEMM is useless.
+// Rows are centred on a fixed point of the reference set (distances are translation invariant), rounded to fp32
+// and split into three bf16 pieces h+m+l (8+8+8 mantissa bits: an exact decomposition of the fp32 value).  The
+// products hh, hm, mh, mm, hl, lh are laid side by side along K (6 d slots), three more slots carry the bf16
+// pieces of ||t||^2 against 1.0, and A is pre-scaled by -2, so that ONE tcgen05.mma chain of K = 80 yields
+//   acc(x,t) = ||t||^2 - 2 x.t      in fp32, to 2^-21 (||x||^2 + ||t||^2)   (all-pairs audit, tests/test_engine_gpu.py)
+// KNN only uses acc as a FILTER: a candidate is re-evaluated exactly (fp64, sklearn's summation order) iff
+// acc <= (worst kept distance - ||x||^2) + kappa (||x||^2 + ||t||^2), kappa = 2^-18; every row the sequential heap
+// would accept passes, every row that passes goes through the same heap_push in index order -> neighbours
+// identical to knn.cu / sklearn.  (The kappa ||t||^2 part is folded into the packed norm: B carries (1-kappa)||t||^2.)
+// SVC uses acc directly: e = -gamma log2(e) (acc + ||x||^2), K = ex2(e), C-1 fp32 FMAs per pair into the running
+// sums of the support vector's class, tile sums promoted to fp64 (tolerance: tests/test_engine_gpu.py).
+//
+// Data layout.  create() packs the reference rows once into tile images of 64 rows x K=80 bf16 in the UMMA
+// canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
+// followed (SVC) by the tile's dual coefficients [C-1][64] fp32.  A tile image is contiguous in HBM, so one
+// cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
+// boundaries (padded with zero-coefficient rows).
+//
+// Kernel (persistent, 1 CTA / SM, 576 threads).  A CTA owns 512 query rows at a time:
+//   warps 0-15  each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
+//               memory, same canonical layout), later reads its accumulator row from TMEM (tcgen05.ld 32x32b)
+//               and runs the KNN filter / SVC exp-and-accumulate epilogue on 64 columns per reference tile;
+//   warp 16     one lane streams reference tile images through a 4-stage ring (bulk copy + mbarrier tx count);
+//   warp 17     one lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per reference tile into a
+//               double-buffered TMEM accumulator (4 tiles x 2 buffers x 64 columns = all 512 columns) and
+//               commits to the ring's "empty" barrier and the accumulator's "full" barrier.
+// Each reference tile (10 KB) is reused by 512 query rows: 16 B/clk/SM of L2 traffic against 640 clk of MMA.
+//
+// A hazard worth writing down (it cost a debugging session on the B200): an mbarrier.arrive does NOT wait for the
+// warp's outstanding ld.shared.  The SVC epilogue reads the dual coefficients out of the ring stage with plain
+// shared loads and then releases the stage; under MUFU pressure those loads can sit in the MIO queue for over a
+// microsecond, the arrive overtakes them, the producer's bulk copy refills the stage and the loads return the NEXT
+// tile's coefficients.  The release is therefore preceded by __threadfence_block() (MEMBAR.CTA waits for the
+// loads to be performed).  tcgen05.ld needs no such care: tcgen05.wait::ld is explicit.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
 #include "common.h"
 
 namespace tcsdn {
 
-int engine_create(tcsdn_model *m) { m->engine = nullptr; return TCSDN_OK; }
-void engine_destroy(tcsdn_model *m) { m->engine = nullptr; }
-bool engine_usable(const tcsdn_model *, int64_t) { return false; }
-int launch_engine(tcsdn_model *, const void *, int64_t, int, int32_t *, double *, cudaStream_t) {
-    set_error("tensor-core engine not built");
-    return TCSDN_EINVAL;
+constexpr int kEThreads = 576;       // 16 epilogue warps + producer warp + MMA warp
+constexpr int kERows = 512;          // query rows per CTA pass (4 MMA tiles of 128)
+constexpr int kEN = 64;              // reference rows per tile (MMA N)
+constexpr int kEK = 80;              // packed K
+constexpr int kEKSteps = kEK / 16;
+constexpr int kEMaxD = 12;           // 6 d + 3 <= 80
+constexpr int kEStages = 4;
+constexpr int kETileB = kEN * kEK * 2;      // 10240 bytes of bf16 per reference tile
+constexpr int kEATile = 128 * kEK * 2;      // 20480 bytes per query tile
+constexpr int kESBO = (kEK / 8) * 128;      // 1280
+constexpr int kEMaxK = 32;                  // neighbours kept per query in the engine
+constexpr int kEMaxNC1 = 7;                 // SVC: n_classes - 1
+constexpr float kKappa = 1.0f / 262144.0f;  // 2^-18: filter slack per unit of (||x||^2 + ||t||^2); 8x the largest error the
+                                            // all-pairs audit observes (2^-21.0 .. 2^-20.4, tests/test_engine_gpu.py)
+constexpr int kEListCap = 64;               // per-thread candidate list (one slot per column of a tile)
+
+struct EngineState {
+    unsigned char *d_tiles = nullptr;   // tile images
+    int32_t *d_tile_class = nullptr;    // per tile: class id (SVC)
+    int32_t *d_tile_row0 = nullptr;     // per tile: index of its first reference row in the ORIGINAL order
+    int32_t *d_tile_rows = nullptr;     // per tile: number of real rows
+    double *d_center = nullptr;         // [d]
+    float *d_maxratio = nullptr;        // audit: max observed |acc - exact| / (||x||^2 + ||t||^2)
+    unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN)
+    int n_tiles = 0;
+    int tile_bytes = 0;
+    int nc1 = 0;
+};
+
+struct EngineArgs {
+    const unsigned char *tiles;
+    const int32_t *tile_class;
+    const int32_t *tile_row0;
+    const int32_t *tile_rows;
+    const double *center;
+    const double *ref;       // original fp64 reference rows (KNN exact re-evaluation)
+    const int32_t *y;        // KNN labels
+    const double *rho;       // SVC
+    float *maxratio;         // non-null = audit mode
+    int32_t *flag;
+    int64_t n;
+    int n_tiles, tile_bytes, d, k, C, nc1;
+    float g2;                // SVC: -gamma * log2(e)
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t e_smem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void e_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(e_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void e_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void e_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e_smem(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU -- after ~2^26 polls the CTA traps (the launch fails loudly).
+__device__ __forceinline__ void e_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(e_smem(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void e_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(e_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(e_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t e_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_NONE: start >> 4 | LBO(128 B) >> 4 << 16 | SBO(1280 B) >> 4 << 32 | version 1 << 46
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(kESBO >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void e_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void e_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(e_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void e_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float e_ex2(float x) {   // one MUFU.EX2 (2 ulp), flushes denormals
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float e_min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+    return r;
+}
+
+// split an fp32 value into three bf16 pieces, exactly: x == h + m + l
+__host__ __device__ __forceinline__ void split3(float x, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l) {
+    h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    l = __float2bfloat16_rn(r2);
+}
+
+// K-slot of (product group g, feature j): A carries [h,h,m,m,h,l], B carries [h,m,h,m,l,h]
+__host__ __device__ __forceinline__ int kslot(int g, int j, int d) { return g * d + j; }
+__host__ __device__ __forceinline__ size_t tile_off(int row, int k) {  // byte offset inside a canonical K-major tile
+    return (size_t)(row >> 3) * kESBO + (size_t)(k >> 3) * 128 + (size_t)(row & 7) * 16 + (size_t)(k & 7) * 2;
+}
+
+// ------------------------------------------------------------------------------------------------ KNN heap
+struct KnnState {
+    double hv[kEMaxK];
+    int32_t hi[kEMaxK];
+    float thr_base;      // (worst kept distance - ||x||^2) + kappa ||x||^2, rounded up
+};
+
+__device__ __forceinline__ void knn_heap_push(double *values, int32_t *indices, int size, double val, int32_t val_idx) {
+    values[0] = val;     // sk:utils/_heap.pyx:6-88 (caller has checked val < values[0])
+    indices[0] = val_idx;
+    int cur = 0;
+    for (;;) {
+        int l = 2 * cur + 1, r = l + 1, swap;
+        if (l >= size) break;
+        if (r >= size) {
+            if (values[l] > val) swap = l; else break;
+        } else if (values[l] >= values[r]) {
+            if (val < values[l]) swap = l; else break;
+        } else {
+            if (val < values[r]) swap = r; else break;
+        }
+        values[cur] = values[swap];
+        indices[cur] = indices[swap];
+        cur = swap;
+    }
+    values[cur] = val;
+    indices[cur] = val_idx;
+}
+
+__device__ __forceinline__ float knn_thr_base(double hv0, double qn) {
+    if (hv0 >= 1e300) return FLT_MAX;
+    return __double2float_ru((hv0 - qn) + (double)kKappa * qn);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <typename T, bool SVC, int NC1>
+__global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X,
+                                                              int32_t *__restrict__ labels, double *__restrict__ scores,
+                                                              unsigned long long *__restrict__ counters) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *sA = smem;                                          // 4 x 20480
+    unsigned char *sB = smem + 4 * kEATile;                            // kEStages x tile_bytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kEStages * A.tile_bytes);
+    uint64_t *fullB = bars, *emptyB = bars + kEStages, *accFull = bars + 2 * kEStages, *accEmpty = accFull + 2;
+    uint64_t *aFull = accEmpty + 2;
+    uint64_t *coefFree = aFull + 1;      // SVC: the 16 epilogue warps are done with a stage's coefficients
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(coefFree + kEStages);
+    unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + 256;   // KNN: [512 threads][kEListCap] column indices
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_super = (A.n + kERows - 1) / kERows;
+
+    if (tid == 0) {
+        for (int s = 0; s < kEStages; ++s) {
+            e_mbar_init(&fullB[s], 1);
+            e_mbar_init(&emptyB[s], 1);      // tcgen05.commit: the MMAs have read the stage
+            e_mbar_init(&coefFree[s], 16);   // SVC: every epilogue warp has read the stage's coefficients
+        }
+        for (int b = 0; b < 2; ++b) {
+            e_mbar_init(&accFull[b], 1);
+            e_mbar_init(&accEmpty[b], 16);
+        }
+        e_mbar_init(aFull, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 17) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(e_smem(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 16) {
+        // ------------------------------------------------------------------ reference tile producer
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+                for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                    e_mbar_wait(&emptyB[s], ph ^ 1);
+                    if (SVC) e_mbar_wait(&coefFree[s], ph ^ 1);
+                    e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
+                    e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)j * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kEN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t g = 0, pass = 0;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
+                e_mbar_wait(aFull, pass & 1);   // the 512 query rows of this pass are packed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                    const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                    e_mbar_wait(&fullB[s], ph);
+                    e_mbar_wait(&accEmpty[b], bph ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bBase = e_smem(sB + (size_t)s * A.tile_bytes);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t aBase = e_smem(sA + t * kEATile);
+                        const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
+#pragma unroll
+                        for (int k = 0; k < kEKSteps; ++k)
+                            e_mma(dcol, e_desc(aBase + k * 256), e_desc(bBase + k * 256), idesc, k > 0);
+                    }
+                    e_commit(&emptyB[s]);    // smem stage may be refilled once these MMAs have read it
+                    e_commit(&accFull[b]);   // accumulators of this reference tile are complete
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ 512 query-row owners (pack A, epilogue)
+        const int qt = warp >> 2;                           // query tile 0..3
+        const int rt = (warp & 3) * 32 + lane;              // row inside the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t g = 0;
+        float nf = 0.f;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+            const int64_t row = st * kERows + qt * 128 + rt;
+            const bool live = row < A.n;
+            // ---- load, centre, split and pack this row into the A operand
+            double q[kEMaxD];
+            double qn = 0.0;
+            {
+                __align__(16) __nv_bfloat16 pk[kEK];
+#pragma unroll
+                for (int i = 0; i < kEK; ++i) pk[i] = __float2bfloat16_rn(0.f);
+#pragma unroll
+                for (int j = 0; j < kEMaxD; ++j) {
+                    q[j] = 0.0;
+                    if (j < A.d && live) {
+                        const T v = X[row * A.d + j];
+                        nf += static_cast<float>(v * static_cast<T>(0));
+                        q[j] = static_cast<double>(v);
+                        const float c32 = static_cast<float>(q[j] - A.center[j]);
+                        qn += (double)c32 * (double)c32;
+                        __nv_bfloat16 h, m, l;
+                        split3(-2.0f * c32, h, m, l);
+                        pk[kslot(0, j, A.d)] = h; pk[kslot(1, j, A.d)] = h; pk[kslot(2, j, A.d)] = m;
+                        pk[kslot(3, j, A.d)] = m; pk[kslot(4, j, A.d)] = h; pk[kslot(5, j, A.d)] = l;
+                    }
+                }
+                const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+                pk[6 * A.d + 0] = one; pk[6 * A.d + 1] = one; pk[6 * A.d + 2] = one;
+                unsigned char *dst = sA + qt * kEATile + (rt >> 3) * kESBO + (rt & 7) * 16;
+#pragma unroll
+                for (int c = 0; c < kEK / 8; ++c)
+                    *reinterpret_cast<uint4 *>(dst + c * 128) = *reinterpret_cast<const uint4 *>(&pk[c * 8]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) e_mbar_arrive(aFull);
+
+            if constexpr (!SVC) {
+                // ================================================================ KNN: filter + exact heap
+                // acc = (1 - kappa) ||t||^2 - 2 x.t, so a row passes iff acc <= thr = (worst kept distance - ||x||^2)
+                // + kappa ||x||^2.  Passing columns are listed per thread, then every lane walks its own list: exact
+                // fp64 distance (sklearn's rdist order) + heap_push, in column = training-index order.
+                KnnState s;
+                for (int i = 0; i < A.k; ++i) { s.hv[i] = DBL_MAX; s.hi[i] = 0; }
+                s.thr_base = FLT_MAX;
+                unsigned long long n_exact = 0;
+                unsigned char *mylist = cand + (size_t)tid * kEListCap;
+                const bool audit = A.maxratio != nullptr;
+                for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                    const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                    e_mbar_wait(&accFull[b], bph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    float v[64];
+                    {
+                        float lo[32], hi[32];
+                        const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
+                        e_tmem_ld32(taddr, lo);
+                        e_tmem_ld32(taddr + 32, hi);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
+                    const float thr = !live ? -FLT_MAX : (audit ? FLT_MAX : s.thr_base);
+                    // group minima first: the common case is "nothing in this group of 8 passes"
+                    uint32_t gmask = 0;
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq) {
+                        const float m0 = e_min3(v[gq * 8 + 0], v[gq * 8 + 1], v[gq * 8 + 2]);
+                        const float m1 = e_min3(v[gq * 8 + 3], v[gq * 8 + 4], v[gq * 8 + 5]);
+                        if (e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7])) <= thr) gmask |= 1u << gq;
+                    }
+                    if (__any_sync(0xffffffffu, gmask != 0)) {
+                        const int nreal = A.tile_rows[j];
+                        int cnt = 0;
+#pragma unroll
+                        for (int gq = 0; gq < 8; ++gq) {
+                            if (!__any_sync(0xffffffffu, (gmask >> gq) & 1u)) continue;
+#pragma unroll
+                            for (int c = gq * 8; c < gq * 8 + 8; ++c) {
+                                const bool pass = ((gmask >> gq) & 1u) && v[c] <= thr && c < nreal;
+                                if (pass) mylist[cnt] = (unsigned char)c;
+                                cnt += pass;
+                            }
+                        }
+                        // every lane walks its own candidates; the loop length is the warp's longest list
+                        const int row0 = A.tile_row0[j];
+                        int longest = cnt;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
+                        for (int i = 0; i < longest; ++i) {
+                            if (i < cnt) {
+                                const int c = mylist[i];
+                                const int32_t idx = row0 + c;
+                                const double *t = A.ref + (size_t)idx * A.d;
+                                double dist = 0.0;
+#pragma unroll
+                                for (int jj = 0; jj < kEMaxD; ++jj)
+                                    if (jj < A.d) {
+                                        const double df = __dsub_rn(q[jj], t[jj]);
+                                        dist = __dadd_rn(dist, __dmul_rn(df, df));
+                                    }
+                                if (audit) {   // error statistic of the tensor-core value (every pair is listed in audit mode)
+                                    float accv = 0.f;
+#pragma unroll
+                                    for (int cc = 0; cc < 64; ++cc) accv = (cc == c) ? v[cc] : accv;
+                                    double tn = 0.0;
+                                    for (int jj = 0; jj < A.d; ++jj) { const double u = t[jj] - A.center[jj]; tn += u * u; }
+                                    const float ratio = (float)(fabs((double)accv - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
+                                    atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
+                                }
+                                ++n_exact;
+                                if (dist < s.hv[0]) {
+                                    knn_heap_push(s.hv, s.hi, A.k, dist, idx);
+                                    s.thr_base = knn_thr_base(s.hv[0], qn);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (live) {
+                    int best = 0, arg = 0;
+                    for (int c = 0; c < A.C; ++c) {
+                        int cnt = 0;
+                        for (int i = 0; i < A.k; ++i) cnt += (A.y[s.hi[i]] == c);
+                        if (scores) scores[row * A.C + c] = (double)cnt / (double)A.k;
+                        if (cnt > best) { best = cnt; arg = c; }
+                    }
+                    labels[row] = arg;
+                    if (counters) atomicAdd(counters, n_exact);
+                }
+            } else {
+                // ================================================================ SVC: exp + one-vs-one sums
+                const float bias = A.g2 * (float)qn;                 // e = g2 * (acc + ||x||^2)
+                const float g2 = A.g2;
+                float tsum[NC1];
+                double csum[NC1];
+                double S[(NC1 + 1) * NC1];                            // S[i][m] = sum_{s in class i} coef[m][s] K_s (local memory)
+#pragma unroll
+                for (int m = 0; m < NC1; ++m) { tsum[m] = 0.f; csum[m] = 0.0; }
+                for (int i = 0; i < (NC1 + 1) * NC1; ++i) S[i] = 0.0;
+                int cur_class = A.tile_class[0];
+                for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                    const uint32_t sidx = g % kEStages;
+                    const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                    const int cls = A.tile_class[j];
+                    if (cls != cur_class) {   // uniform across the CTA: support vectors are grouped by class
+#pragma unroll
+                        for (int m = 0; m < NC1; ++m) { S[cur_class * NC1 + m] = csum[m]; csum[m] = 0.0; }
+                        cur_class = cls;
+                    }
+                    e_mbar_wait(&accFull[b], bph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // the coefficients were written by the bulk copy (async proxy): observe ITS barrier before reading them
+                    // (already complete here -- the MMAs consumed the same stage -- so this never blocks)
+                    e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
+                    const float *coef = reinterpret_cast<const float *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
+                    const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float v[32];
+                        e_tmem_ld32(taddr + h * 32, v);
+                        if (h == 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) e_mbar_arrive(&accEmpty[b]);
+                        }
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            float4 cf[NC1];
+#pragma unroll
+                            for (int m = 0; m < NC1; ++m)
+                                cf[m] = *reinterpret_cast<const float4 *>(coef + m * kEN + h * 32 + c4 * 4);
+                            const float k0 = e_ex2(fmaf(v[c4 * 4 + 0], g2, bias));
+                            const float k1 = e_ex2(fmaf(v[c4 * 4 + 1], g2, bias));
+                            const float k2 = e_ex2(fmaf(v[c4 * 4 + 2], g2, bias));
+                            const float k3 = e_ex2(fmaf(v[c4 * 4 + 3], g2, bias));
+#pragma unroll
+                            for (int m = 0; m < NC1; ++m) {
+                                tsum[m] = fmaf(cf[m].x, k0, tsum[m]);
+                                tsum[m] = fmaf(cf[m].y, k1, tsum[m]);
+                                tsum[m] = fmaf(cf[m].z, k2, tsum[m]);
+                                tsum[m] = fmaf(cf[m].w, k3, tsum[m]);
+                            }
+                        }
+                    }
+                    // Release the stage only after every coefficient load has actually been PERFORMED: mbarrier.arrive does
+                    // not wait for outstanding ld.shared (see the file header); MEMBAR.CTA does.
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) e_mbar_arrive(&coefFree[sidx]);
+#pragma unroll
+                    for (int m = 0; m < NC1; ++m) { csum[m] += (double)tsum[m]; tsum[m] = 0.f; }
+                }
+#pragma unroll
+                for (int m = 0; m < NC1; ++m) S[cur_class * NC1 + m] = csum[m];
+                if (live) {
+                    constexpr int C = NC1 + 1, P = C * (C - 1) / 2;
+                    int vote[C];
+                    for (int c = 0; c < C; ++c) vote[c] = 0;
+                    int p = 0;
+                    for (int i = 0; i < C; ++i)
+                        for (int jj = i + 1; jj < C; ++jj) {
+                            const double dv = (S[i * NC1 + (jj - 1)] + S[jj * NC1 + i]) - A.rho[p];
+                            if (scores) scores[row * P + p] = dv;
+                            if (dv > 0) ++vote[i]; else ++vote[jj];
+                            ++p;
+                        }
+                    int arg = 0;
+                    for (int c = 1; c < C; ++c)
+                        if (vote[c] > vote[arg]) arg = c;
+                    labels[row] = arg;
+                }
+            }
+        }
+        if (A.flag && nf != nf) atomicOr(A.flag, 1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 17) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void pack_row(unsigned char *tile, int r, const double *x, const double *center, int d, double norm_scale) {
+    double nrm = 0.0;
+    float c32[kEMaxD];
+    for (int j = 0; j < d; ++j) {
+        c32[j] = static_cast<float>(x[j] - center[j]);
+        nrm += (double)c32[j] * (double)c32[j];
+    }
+    auto put = [&](int k, __nv_bfloat16 v) { memcpy(tile + tile_off(r, k), &v, 2); };
+    for (int j = 0; j < d; ++j) {
+        __nv_bfloat16 h, m, l;
+        split3(c32[j], h, m, l);
+        put(kslot(0, j, d), h); put(kslot(1, j, d), m); put(kslot(2, j, d), h);
+        put(kslot(3, j, d), m); put(kslot(4, j, d), l); put(kslot(5, j, d), h);
+    }
+    __nv_bfloat16 h, m, l;
+    split3(static_cast<float>(nrm * norm_scale), h, m, l);   // KNN folds the filter slack in: (1 - kappa) ||t||^2
+    put(6 * d + 0, h); put(6 * d + 1, m); put(6 * d + 2, l);
+}
+
+static void pack_dummy(unsigned char *tile, int r, int d) {  // a row that is "infinitely" far from everything
+    const __nv_bfloat16 big = __float2bfloat16_rn(1e30f);
+    memcpy(tile + tile_off(r, 6 * d + 0), &big, 2);
+}
+
+int engine_create(tcsdn_model *m) {
+    m->engine = nullptr;
+    const int d = m->d;
+    if (d > kEMaxD) return TCSDN_OK;                       // engine not applicable: fp64 kernels only
+    const bool svc = m->kind == TCSDN_KIND_SVC;
+    if (!svc && m->k > kEMaxK) return TCSDN_OK;
+    if (svc && m->n_classes - 1 > kEMaxNC1) return TCSDN_OK;
+    const int64_t nref = svc ? m->n_sv : m->n_train;
+    std::vector<double> ref((size_t)nref * d);
+    TCSDN_CUDA(cudaMemcpy(ref.data(), svc ? m->d_sv : m->d_fit, ref.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // Centre: the coordinate-wise median.  Any fixed point is correct; the tensor-core error scales with
+    // ||x-c||^2 + ||t-c||^2, and flow features are heavy-tailed (most rows sit near small values, a few classes reach
+    // 1e4..1e5): the median keeps the norms of the dense small-valued clusters small, the mean does not.
+    std::vector<double> center(d, 0.0), col((size_t)nref);
+    for (int j = 0; j < d; ++j) {
+        for (int64_t i = 0; i < nref; ++i) col[(size_t)i] = ref[(size_t)i * d + j];
+        std::nth_element(col.begin(), col.begin() + nref / 2, col.end());
+        center[j] = col[(size_t)(nref / 2)];
+    }
+
+    EngineState *E = new EngineState();
+    const int nc1 = svc ? m->n_classes - 1 : 0;
+    E->nc1 = nc1;
+    E->tile_bytes = kETileB + nc1 * kEN * (int)sizeof(float);
+    // tile plan: KNN = consecutive rows; SVC = per class, padded to a tile boundary
+    std::vector<int32_t> row0, rows, tclass;
+    if (!svc) {
+        for (int64_t r = 0; r < nref; r += kEN) { row0.push_back((int32_t)r); rows.push_back((int32_t)std::min<int64_t>(kEN, nref - r)); tclass.push_back(0); }
+    } else {
+        std::vector<int32_t> start(m->n_classes + 1);
+        TCSDN_CUDA(cudaMemcpy(start.data(), m->d_start, start.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < m->n_classes; ++c)
+            for (int r = start[c]; r < start[c + 1]; r += kEN) {
+                row0.push_back(r); rows.push_back(std::min(kEN, start[c + 1] - r)); tclass.push_back(c);
+            }
+    }
+    E->n_tiles = (int)row0.size();
+    std::vector<unsigned char> img((size_t)E->n_tiles * E->tile_bytes, 0);
+    std::vector<double> coef;
+    if (svc) {
+        coef.resize((size_t)nc1 * nref);
+        TCSDN_CUDA(cudaMemcpy(coef.data(), m->d_coef, coef.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    for (int t = 0; t < E->n_tiles; ++t) {
+        unsigned char *tile = img.data() + (size_t)t * E->tile_bytes;
+        for (int r = 0; r < kEN; ++r) {
+            if (r < rows[t]) {
+                pack_row(tile, r, &ref[(size_t)(row0[t] + r) * d], center.data(), d, svc ? 1.0 : 1.0 - (double)kKappa);
+                if (svc) {
+                    float *cf = reinterpret_cast<float *>(tile + kETileB);
+                    for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + row0[t] + r]);
+                }
+            } else {
+                pack_dummy(tile, r, d);
+            }
+        }
+    }
+    int rc = upload(&E->d_tiles, img.data(), img.size());
+    if (rc == TCSDN_OK) rc = upload(&E->d_tile_class, tclass.data(), tclass.size());
+    if (rc == TCSDN_OK) rc = upload(&E->d_tile_row0, row0.data(), row0.size());
+    if (rc == TCSDN_OK) rc = upload(&E->d_tile_rows, rows.data(), rows.size());
+    if (rc == TCSDN_OK) rc = upload(&E->d_center, center.data(), center.size());
+    float zero = 0.f;
+    unsigned long long zero64 = 0;
+    if (rc == TCSDN_OK) rc = upload(&E->d_maxratio, &zero, 1);
+    if (rc == TCSDN_OK) rc = upload(&E->d_counters, &zero64, 1);
+    m->engine = E;
+    if (rc != TCSDN_OK) { engine_destroy(m); return rc; }
+    return TCSDN_OK;
+}
+
+void engine_destroy(tcsdn_model *m) {
+    EngineState *E = static_cast<EngineState *>(m->engine);
+    if (!E) return;
+    cudaFree(E->d_tiles); cudaFree(E->d_tile_class); cudaFree(E->d_tile_row0); cudaFree(E->d_tile_rows);
+    cudaFree(E->d_center); cudaFree(E->d_maxratio); cudaFree(E->d_counters);
+    delete E;
+    m->engine = nullptr;
+}
+
+bool engine_usable(const tcsdn_model *m, int64_t n) {
+    if (!m->engine) return false;
+    if (m->opt_engine >= 2) return true;
+    return n >= 4096;   // below this the fp64 CUDA-core kernels (latency path) are faster than filling 148 SMs x 512 rows
+}
+
+template <typename T>
+static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+    EngineState *E = static_cast<EngineState *>(m->engine);
+    const bool svc = m->kind == TCSDN_KIND_SVC;
+    EngineArgs A;
+    A.tiles = E->d_tiles; A.tile_class = E->d_tile_class; A.tile_row0 = E->d_tile_row0;
+    A.tile_rows = E->d_tile_rows; A.center = E->d_center; A.ref = m->d_fit; A.y = m->d_y; A.rho = m->d_rho;
+    // audit mode (engine option 3): the KNN filter is disabled so that EVERY pair is re-evaluated exactly, and the
+    // largest |tensor-core value - exact| / (||x||^2 + ||t||^2) is recorded (stats[5]); tests only
+    A.maxratio = m->opt_engine == 3 ? E->d_maxratio : nullptr;
+    A.flag = m->opt_check_finite ? m->d_flag : nullptr; A.n = n; A.n_tiles = E->n_tiles;
+    A.tile_bytes = E->tile_bytes; A.d = m->d; A.k = m->k; A.C = m->n_classes; A.nc1 = E->nc1;
+    A.g2 = static_cast<float>(-m->gamma * 1.4426950408889634);
+    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 + (svc ? 0 : 512 * (size_t)kEListCap);
+    const int64_t n_super = (n + kERows - 1) / kERows;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_super, m->sm_count);
+#define TCSDN_LAUNCH(SVCF, NC)                                                                                    \
+    {                                                                                                             \
+        auto kern = engine_kernel<T, SVCF, NC>;                                                                   \
+        TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        kern<<<grid, kEThreads, smem, st>>>(A, x, labels, scores, E->d_counters);                                 \
+    }
+    if (!svc) TCSDN_LAUNCH(false, 1)
+    else switch (E->nc1) {
+        case 1: TCSDN_LAUNCH(true, 1) break;
+        case 2: TCSDN_LAUNCH(true, 2) break;
+        case 3: TCSDN_LAUNCH(true, 3) break;
+        case 4: TCSDN_LAUNCH(true, 4) break;
+        case 5: TCSDN_LAUNCH(true, 5) break;
+        case 6: TCSDN_LAUNCH(true, 6) break;
+        case 7: TCSDN_LAUNCH(true, 7) break;
+        default: set_error("svc engine: unsupported class count"); return TCSDN_EINVAL;
+    }
+#undef TCSDN_LAUNCH
+    TCSDN_CUDA(cudaGetLastError());
+    m->stats[0] += 1;
+    m->stats[1] += n;
+    return TCSDN_OK;
+}
+
+int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores, cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    if (dtype == TCSDN_F32) return launch_engine_t<float>(m, static_cast<const float *>(x), n, labels, scores, st);
+    return launch_engine_t<double>(m, static_cast<const double *>(x), n, labels, scores, st);
+}
+
+// cumulative engine counters since create(): exact re-evaluations, max error ratio * 2^40 (synchronising read)
+void engine_read_stats(const tcsdn_model *m, int64_t *exact_evals, int64_t *maxratio_q40) {
+    *exact_evals = 0; *maxratio_q40 = 0;
+    EngineState *E = static_cast<EngineState *>(m->engine);
+    if (!E) return;
+    unsigned long long c = 0;
+    float v = 0.f;
+    if (cudaMemcpy(&c, E->d_counters, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) *exact_evals = (int64_t)c;
+    if (cudaMemcpy(&v, E->d_maxratio, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) *maxratio_q40 = (int64_t)((double)v * 1099511627776.0);
 }
 
 }  // namespace tcsdn

@@ -2,10 +2,11 @@
 //
 // One flow row is 32-96 bytes and is touched once, the model is a few hundred doubles: these three
 // estimators are HBM-bound streams.  Layout: rows stay row-major in HBM exactly as the caller has
-// them; a persistent CTA pulls 256-row tiles into a 4-deep shared-memory ring with 1-D bulk async
-// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), each thread lifts one row out of
-// shared memory with conflict-free 128-bit loads, scores it in fp64 against parameters that sit in
-// the constant bank (kernel parameters, __grid_constant__) and writes one int32 label.
+// them; a persistent CTA pulls 512-row tiles into a 3-deep shared-memory ring with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), each thread lifts four rows out of
+// shared memory with conflict-free 128-bit loads, scores them in fp64 against parameters that sit in
+// the constant bank (kernel parameters, __grid_constant__; fetched once per four rows) and writes
+// four int32 labels.
 // Algorithmic bytes per row: d*sizeof(T) in + 4 out.
 //
 //   linear : sk:linear_model/_base.py:391 (X @ coef_.T + intercept_), :418 argmax / :416 (score > 0)
@@ -26,8 +27,10 @@
 
 namespace tcsdn {
 
-constexpr int kTile = 256;    // rows per tile == threads per CTA
-constexpr int kStages = 4;
+constexpr int kThreads = 128;  // threads per CTA
+constexpr int kRPT = 4;        // rows per thread: the model's constants are fetched once per 4 rows
+constexpr int kTile = kThreads * kRPT;   // rows per tile
+constexpr int kStages = 3;
 
 enum : int { KIND_AFFINE_MAX = 0, KIND_AFFINE_MIN = 1, KIND_GNB = 2 };
 
@@ -82,36 +85,53 @@ __device__ __forceinline__ void load_row_smem(const T *tile, int r, double (&x)[
     }
 }
 
+// Scores kRPT rows at once: for every (class r, feature j) the constants are read once and applied to all rows,
+// which keeps the constant-bank traffic (one LDC per operand) off the fp64 pipe's critical path.
 template <int D, int R, int KIND>
-__device__ __forceinline__ int score_row(const ScorerParams &P, const double (&x)[D], double (&s)[R]) {
-    int arg = 0;
-    double best = 0.0;
+__device__ __forceinline__ void score_rows(const ScorerParams &P, const double (&x)[kRPT][D], double (&s)[kRPT][R],
+                                           int (&arg)[kRPT]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        double acc = P.c[r];
-        if constexpr (KIND == KIND_GNB) {
+        double acc[kRPT];
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const double t = fma(x[j], P.a[r * D + j], -P.b[r * D + j]);   // (x - theta) / sqrt(2 var)
-                acc = fma(-t, t, acc);
+        for (int q = 0; q < kRPT; ++q) acc[q] = P.c[r];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double ca = P.a[r * D + j];
+            if constexpr (KIND == KIND_GNB) {
+                const double cb = -P.b[r * D + j];
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q) {
+                    const double t = fma(x[q][j], ca, cb);   // (x - theta) / sqrt(2 var)
+                    acc[q] = fma(-t, t, acc[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q) acc[q] = fma(x[q][j], ca, acc[q]);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < D; ++j) acc = fma(x[j], P.a[r * D + j], acc);
         }
-        s[r] = acc;
-        bool better = (KIND == KIND_AFFINE_MIN) ? (acc < best) : (acc > best);
-        if (r == 0 || better) { best = acc; arg = r; }
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) s[q][r] = acc[q];
     }
-    if (R == 1 && KIND == KIND_AFFINE_MAX) arg = s[0] > 0.0 ? 1 : 0;
-    return arg;
+#pragma unroll
+    for (int q = 0; q < kRPT; ++q) {
+        int a = 0;
+        double best = s[q][0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const bool better = (KIND == KIND_AFFINE_MIN) ? (s[q][r] < best) : (s[q][r] > best);
+            if (better) { best = s[q][r]; a = r; }
+        }
+        if (R == 1 && KIND == KIND_AFFINE_MAX) a = s[q][0] > 0.0 ? 1 : 0;
+        arg[q] = a;
+    }
 }
 
 template <typename T, int D, int R, int KIND>
-__global__ void __launch_bounds__(kTile) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
-                                                             const T *__restrict__ X, int64_t n,
-                                                             int32_t *__restrict__ labels,
-                                                             double *__restrict__ scores, int32_t *flag) {
+__global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
+                                                                const T *__restrict__ X, int64_t n,
+                                                                int32_t *__restrict__ labels,
+                                                                double *__restrict__ scores, int32_t *flag) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
     T *tiles = reinterpret_cast<T *>(smem_raw);
@@ -152,26 +172,38 @@ __global__ void __launch_bounds__(kTile) scorer_tiled_kernel(const __grid_consta
         const int stage = it % kStages;
         const uint32_t parity = (it / kStages) & 1;
         mbar_wait(&full[stage], parity);
-        const int64_t row = tile * kTile + tid;
-        const bool live = row < n;
-        double x[D];
-        if (live) {
-            load_row_smem<T, D>(reinterpret_cast<const T *>(reinterpret_cast<unsigned char *>(tiles) +
-                                                            (size_t)stage * kTileBytes),
-                                tid, x, nf);
+        const int64_t row0 = tile * kTile;
+        const T *tp = reinterpret_cast<const T *>(reinterpret_cast<unsigned char *>(tiles) + (size_t)stage * kTileBytes);
+        double x[kRPT][D];
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) {   // thread t owns rows t, t+128, t+256, t+384 of the tile (conflict-free 16 B loads)
+            if (row0 + q * kThreads + tid < n) load_row_smem<T, D>(tp, q * kThreads + tid, x[q], nf);
+            else {
+#pragma unroll
+                for (int j = 0; j < D; ++j) x[q][j] = 0.0;
+            }
         }
-        __syncthreads();  // every thread has lifted its row: the stage may be refilled
+        // The stage is refilled by the async proxy (bulk copy) right after this barrier.  BAR.SYNC orders generic-proxy
+        // accesses among threads, but the bulk copy must not overtake shared loads that are still in flight, so every
+        // thread first makes sure its loads have been performed (MEMBAR.CTA; see dist_engine.cu for the hazard).
+        __threadfence_block();
+        __syncthreads();  // every thread has lifted its rows: the stage may be refilled
         if (tid == 0) {
             int64_t nt = tile + (int64_t)kStages * stride;
             if (nt < n_tiles) issue(nt, stage);
         }
-        if (live) {
-            double s[R];
-            int arg = score_row<D, R, KIND>(P, x, s);
-            labels[row] = arg;
-            if (scores) {
+        double s[kRPT][R];
+        int arg[kRPT];
+        score_rows<D, R, KIND>(P, x, s, arg);
 #pragma unroll
-                for (int r = 0; r < R; ++r) scores[row * R + r] = s[r];
+        for (int q = 0; q < kRPT; ++q) {
+            const int64_t row = row0 + q * kThreads + tid;
+            if (row < n) {
+                labels[row] = arg[q];
+                if (scores) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) scores[row * R + r] = s[q][r];
+                }
             }
         }
     }
@@ -224,10 +256,10 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
         configured = true;
     }
     int64_t n_tiles = (n + kTile - 1) / kTile;
-    int ctas_per_sm = sizeof(T) == 4 ? 4 : 2;
+    int ctas_per_sm = sizeof(T) == 4 ? 3 : 2;
     int64_t grid = (int64_t)m->sm_count * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    kern<<<(unsigned)grid, kTile, smem, st>>>(m->sp, x, n, labels, scores, flag);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
 }
