@@ -82,8 +82,7 @@ def build_workload(name, quick=False):
     if name == "knn":
         Xtr, ytr = synth.make_flows(50_000, seed=seed + 2)
         spec = dict(kind="knn", fit_X=Xtr, y=ytr.astype(np.int32), k=5, classes=synth.CLASSES, n_features=12)
-        full = os.environ.get("TCSDN_BENCH_FULL", "0") == "1"
-        return dict(spec=spec, sk=None, d=12, rows=(10_000_000 if full else 200_000) if not quick else 20_000, bytes_per_row=52,
+        return dict(spec=spec, sk=None, d=12, rows=10_000_000 if not quick else 200_000, bytes_per_row=52,
                     flops_per_row=2 * 12 * 50_000, desc="KNeighbors k=5 brute force, 10M queries x 50k train rows "
                     "(BASELINE configs[2])", bound="tensor", cpu_sample_rows=20_000)
     if name == "svc":
@@ -98,8 +97,7 @@ def build_workload(name, quick=False):
         spec = dict(kind="svc", sv=Xs, dual_coef=dual, intercept=rng.normal(0, 0.5, C * (C - 1) // 2), n_support=nsup,
                     gamma=float(gamma), classes=synth.CLASSES, n_features=12, decision_function_shape="ovr",
                     break_ties=False, n_classes=C)
-        full = os.environ.get("TCSDN_BENCH_FULL", "0") == "1"
-        return dict(spec=spec, sk=None, d=12, rows=(10_000_000 if full else 100_000) if not quick else 10_000, bytes_per_row=52,
+        return dict(spec=spec, sk=None, d=12, rows=10_000_000 if not quick else 200_000, bytes_per_row=52,
                     flops_per_row=2 * 12 * nsv + 2 * (C - 1) * nsv, desc="SVC(rbf) 10M flows x 20k support vectors, "
                     "6 classes (BASELINE configs[3])", bound="tensor", cpu_sample_rows=4_000)
     raise ValueError(name)
@@ -383,11 +381,6 @@ def main():
         for name in [x for x in args.extras.split(",") if x and x != args.workload]:
             try:
                 wx = build_workload(name, args.quick)
-                # the fp64 CUDA-core kernels for knn / svc are the small-batch path: until the tensor-core
-                # engine takes a batch, measure them on a stated, reduced number of rows
-                from traffic_classifier_sdn_b200 import from_spec  # noqa: F401
-                if name in ("knn", "svc") and wx["rows"] < 10_000_000:
-                    wx["desc"] += f" -- REDUCED to {wx['rows']} rows/step (fp64 CUDA-core kernels; tensor-core engine pending)"
                 steps_x = max(3, min(args.steps, 5))
                 r = measure_gpu(wx, steps_x, 3, world, device, peaks, extras_light=True)
                 entry = {"workload": wx["desc"], "value": r["value"], "unit": "flow-rows/s", "rows_per_gpu_per_step": r["rows"],

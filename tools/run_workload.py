@@ -6,7 +6,6 @@ import torch
 import bench
 from traffic_classifier_sdn_b200 import from_spec
 name, rows = sys.argv[1], int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-os.environ["TCSDN_BENCH_FULL"] = "1"
 w = bench.build_workload(name)
 est = from_spec(w["spec"])
 X = bench.synth_rows(rows, w["d"], seed=1000, device=torch.device("cuda", 0))
