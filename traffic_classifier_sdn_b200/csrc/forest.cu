@@ -34,8 +34,7 @@ constexpr int kFThreads = 512;
 constexpr int kRPT = 2;                       // rows per thread
 constexpr int kFRows = kFThreads * kRPT;      // rows per tile
 constexpr uint32_t kLeaf = 0x80000000u;
-constexpr uint32_t kPure = 0x00800000u;
-constexpr uint32_t kEnd = 0xFFFFFFFFu;      // 'no next tree' marker in a leaf's x field
+constexpr uint32_t kNegInf = 0xFF800000u;   // x of a pure leaf and of the halt node; impure leaves use 0xFFC00000 | index
 
 struct ForestArgs {
     const uint2 *nodes;
@@ -48,13 +47,19 @@ struct ForestArgs {
 };
 
 // One chain = one row walking the trees of a group back to back.  `pos` is the node index relative to the
-// group's first node.
-//   internal node: x = threshold (fp32), y = feature << 24 | distance to the right child (left child = pos + 1)
-//   leaf:          y bit 31 set, bits 30..24 zero (so the "feature" of a leaf reads as 0 and needs no masking),
-//                  bit 23 = pure, low 23 bits = class (pure) or index into the fraction table (impure);
-//                  x = position of the NEXT tree's root, or kEnd after the group's last tree.
-// The body is branch-free for internal nodes and pure leaves: the accumulator read-modify-write is
-// predicated inline PTX, so lanes sitting on a leaf never serialise the warp.  Impure leaves (rare) branch.
+// group's first node.  The encoding makes leaves look like internal nodes to the position update, so the loop
+// body has no leaf/internal branch at all:
+//   internal: x = threshold (fp32, rounded down), y = feature << 24 | distance to the right child (left = pos + 1)
+//   leaf:     x = -inf (pure) or a quiet NaN whose payload indexes the fraction table (impure): `v <= x` is false
+//             for every finite v, so the step taken is y's low 24 bits = distance to the NEXT tree's root;
+//             y = 1 << 31 | class << 24 | jump.  The class sits where internal nodes keep the feature, so the same
+//             index arithmetic addresses xs[feature][row] and acc[class][row] (xs has max(d, C) rows).
+//   halt:     the node after the group's last tree: x = -inf, y = 0 -> a self loop that is not a leaf.  The last
+//             tree's leaves jump to it; finished chains spin on it harmlessly, so the exit test runs once per
+//             kUnroll steps instead of per step.
+// Pure leaves accumulate with predicated inline PTX (no branch); impure leaves (rare) take a real branch.
+constexpr int kUnroll = 4;
+
 __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
     asm volatile(
         "{\n"
@@ -70,43 +75,40 @@ __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
 }
 
 template <bool IN_SMEM>
-__device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, const float *xs, double *acc,
+__device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_t halt, const float *xs, double *acc,
                                            const double *leaf_val, int C, int r0, int nrows_live) {
     uint32_t pos[kRPT];
-    bool act[kRPT];
-    bool any = false;
     const uint32_t acc_base = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
 #pragma unroll
-    for (int q = 0; q < kRPT; ++q) {
-        pos[q] = 0;
-        act[q] = (r0 + q * kFThreads) < nrows_live;
-        any |= act[q];
-    }
-    while (any) {
-        uint2 nd[kRPT];
+    for (int q = 0; q < kRPT; ++q) pos[q] = (r0 + q * kFThreads) < nrows_live ? 0u : halt;
+    for (;;) {
 #pragma unroll
-        for (int q = 0; q < kRPT; ++q) nd[q] = np[act[q] ? pos[q] : 0u];
-        any = false;
+        for (int u = 0; u < kUnroll; ++u) {
+            uint2 nd[kRPT];
 #pragma unroll
-        for (int q = 0; q < kRPT; ++q) {
-            const uint32_t r = (uint32_t)(r0 + q * kFThreads);
-            const uint32_t y = nd[q].y;
-            const bool leaf = (int32_t)y < 0;
-            const float x = xs[((y >> 24) & 0x7Fu) * kFRows + r];
-            const uint32_t step = (x <= __uint_as_float(nd[q].x)) ? 1u : (y & 0xFFFFFFu);
-            const bool pure = ((y & (kLeaf | kPure)) == (kLeaf | kPure)) && act[q];
-            acc_add_one_if(acc_base + (((y & 0xFFu) * kFRows + r) << 3), pure);
-            if (leaf && !(y & kPure) && act[q]) {
-                const double *lv = leaf_val + (size_t)(y & 0x7FFFFFu) * C;
-                for (int c = 0; c < C; ++c) {
-                    double v = lv[c];
-                    if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
+            for (int q = 0; q < kRPT; ++q) nd[q] = np[pos[q]];
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) {
+                const uint32_t r = (uint32_t)(r0 + q * kFThreads);
+                const uint32_t y = nd[q].y;
+                const uint32_t slot = ((y >> 24) & 0x7Fu) * kFRows + r;          // xs[feature][r] / acc[class][r]
+                const float x = xs[slot];
+                const uint32_t step = (x <= __uint_as_float(nd[q].x)) ? 1u : (y & 0xFFFFFFu);
+                acc_add_one_if(acc_base + (slot << 3), ((int32_t)y < 0) & (nd[q].x == kNegInf));
+                if (((int32_t)y < 0) & (nd[q].x > kNegInf)) {                    // impure leaf: NaN payload = table index
+                    const double *lv = leaf_val + (size_t)(nd[q].x & 0x3FFFFFu) * C;
+                    for (int c = 0; c < C; ++c) {
+                        double v = lv[c];
+                        if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
+                    }
                 }
+                pos[q] += step;
             }
-            pos[q] = leaf ? nd[q].x : pos[q] + step;
-            act[q] = act[q] && (pos[q] != kEnd);
-            any |= act[q];
         }
+        bool done = true;
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) done &= (pos[q] == halt);
+        if (done) break;
     }
 }
 
@@ -117,18 +119,22 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
                                                               double *__restrict__ proba, int32_t *flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int d = A.d, C = A.C;
-    float *xs = reinterpret_cast<float *>(smem_raw);                       // [d][kFRows]
-    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)d * kFRows * 4);  // [C][kFRows]
-    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + (size_t)d * kFRows * 4 + (size_t)C * kFRows * 8);
+    const int xrows = d > C ? d : C;                                        // leaves read xs[class][row] (value unused)
+    float *xs = reinterpret_cast<float *>(smem_raw);                       // [max(d,C)][kFRows]
+    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)xrows * kFRows * 4);  // [C][kFRows]
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + (size_t)xrows * kFRows * 4 + (size_t)C * kFRows * 8);
     __shared__ int32_t s_tb[1];  // placeholder to keep static smem non-empty (tree_base is read from L1)
 
     const int tid = threadIdx.x;
     const int64_t n_tiles = (A.n + kFRows - 1) / kFRows;
-    const bool single = (A.n_groups == 1) && (A.tree_base[A.n_trees] <= A.node_cap);
+    // node array layout: each group's trees followed by its halt node -> group g starts at tree_base[first tree] + g
+    const bool single = (A.n_groups == 1) && (A.tree_base[A.n_trees] + 1 <= A.node_cap);
     if (single) {
-        const int nn = A.tree_base[A.n_trees];
+        const int nn = A.tree_base[A.n_trees] + 1;
         for (int i = tid; i < nn; i += kFThreads) snodes[i] = A.nodes[i];
     }
+    if (xrows > d)
+        for (int i = tid; i < (xrows - d) * kFRows; i += kFThreads) xs[d * kFRows + i] = 0.f;
     float nf = 0.f;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kFRows;
@@ -151,8 +157,8 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
         }
         for (int g = 0; g < A.n_groups; ++g) {
             const int t_begin = A.group_begin[g], t_end = A.group_begin[g + 1];
-            const int node0 = A.tree_base[t_begin];
-            const int gn = A.tree_base[t_end] - node0;
+            const int node0 = A.tree_base[t_begin] + g;                   // g halt nodes precede this group
+            const int gn = A.tree_base[t_end] - A.tree_base[t_begin] + 1; // trees + halt node
             const bool in_smem = gn <= A.node_cap;
             if (!single && in_smem) {
                 __syncthreads();  // everyone is done with the previous group's nodes
@@ -160,9 +166,9 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             }
             __syncthreads();
             if (in_smem)
-                walk_group<true>(snodes, xs, acc, A.leaf_val, C, tid, live);
+                walk_group<true>(snodes, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
             else
-                walk_group<false>(A.nodes + node0, xs, acc, A.leaf_val, C, tid, live);
+                walk_group<false>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
         }
         // each thread finalises its own rows (only it touched their accumulators)
 #pragma unroll
@@ -193,16 +199,16 @@ static float floor32(double t) {
 int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left, const int32_t *right,
                 const int32_t *feature, const double *threshold, const double *value, int n_trees, int C) {
     const int d = m->d;
-    if (d > 127 || C > 255) { set_error("forest: n_features must be <= 127 and n_classes <= 255"); return TCSDN_EINVAL; }
+    if (d > 127 || C > 127) { set_error("forest: n_features and n_classes must be <= 127"); return TCSDN_EINVAL; }
     int dev_smem = 0;
     TCSDN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->dev));
-    const int64_t fixed = (int64_t)d * kFRows * 4 + (int64_t)C * kFRows * 8 + 1024;
+    const int64_t fixed = (int64_t)(d > C ? d : C) * kFRows * 4 + (int64_t)C * kFRows * 8 + 1024;
     if (fixed + 8 * 64 > dev_smem) {
         set_error("forest: d=%d, n_classes=%d need %lld bytes of shared memory per tile (device has %d)", d, C,
                   (long long)fixed, dev_smem);
         return TCSDN_EINVAL;
     }
-    m->group_node_cap = (int)((dev_smem - fixed) / 8);
+    m->group_node_cap = (int)((dev_smem - fixed) / 8) - 1;   // one slot per group is the halt node
 
     std::vector<uint2> nodes;
     std::vector<int32_t> tree_base(1, 0), group_begin(1, 0);
@@ -243,13 +249,15 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
                     if (v[c] == 1.0) { ones++; cls = c; }
                     else if (v[c] == 0.0) zeros++;
                 }
-                nd.x = 0;  // next-tree root, patched once the groups are known
+                // y's low 24 bits (jump to the next tree's root) are patched once the groups are known
                 if (ones == 1 && zeros == C - 1) {
-                    nd.y = kLeaf | kPure | (uint32_t)cls;
+                    nd.x = kNegInf;
+                    nd.y = kLeaf | ((uint32_t)cls << 24);
                 } else {
                     const size_t li = leaf_val.size() / C;
-                    if (li >= (1u << 23)) { set_error("forest: more than 2^23 impure leaves"); return TCSDN_EINVAL; }
-                    nd.y = kLeaf | (uint32_t)li;
+                    if (li >= (1u << 22)) { set_error("forest: more than 2^22 impure leaves"); return TCSDN_EINVAL; }
+                    nd.x = 0xFFC00000u | (uint32_t)li;   // quiet NaN: never <= anything
+                    nd.y = kLeaf;                          // class field 0: xs[0][row] is read and ignored
                     leaf_val.insert(leaf_val.end(), v, v + C);
                 }
             } else {
@@ -284,19 +292,31 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
         tree_base.push_back((int32_t)nodes.size());
     }
     group_begin.push_back(n_trees);
-    // every leaf points at the root of the next tree of its group (position relative to the group's first node)
+    // Every leaf jumps to the root of the next tree of its group; the last tree's leaves jump to the group's halt
+    // node, which is appended right after the group (so group g is shifted by g slots in the device array).
+    std::vector<uint2> laid;
+    laid.reserve(nodes.size() + group_begin.size());
     for (size_t g = 0; g + 1 < group_begin.size(); ++g) {
         const int tb = group_begin[g], te = group_begin[g + 1];
-        const int32_t node0 = tree_base[tb];
         for (int t = tb; t < te; ++t) {
-            const uint32_t next = (t + 1 < te) ? (uint32_t)(tree_base[t + 1] - node0) : kEnd;
-            for (int32_t i = tree_base[t]; i < tree_base[t + 1]; ++i)
-                if (nodes[i].y & kLeaf) nodes[i].x = next;
+            const int32_t next_root = tree_base[t + 1];   // == halt position for the last tree (relative numbering agrees)
+            for (int32_t i = tree_base[t]; i < tree_base[t + 1]; ++i) {
+                uint2 nd = nodes[i];
+                if (nd.y & kLeaf) {
+                    const int64_t jump = (int64_t)next_root - i;
+                    if (jump < 1 || jump >= (1 << 24)) { set_error("forest: tree %d too large to encode", t); return TCSDN_EINVAL; }
+                    nd.y |= (uint32_t)jump;
+                }
+                laid.push_back(nd);
+            }
         }
+        uint2 halt; halt.x = kNegInf; halt.y = 0;
+        laid.push_back(halt);
     }
+    nodes.swap(laid);
     m->n_trees = n_trees;
     m->n_groups = (int)group_begin.size() - 1;
-    m->n_nodes = (int64_t)nodes.size();
+    m->n_nodes = (int64_t)nodes.size();   // including one halt node per group
     if (leaf_val.empty()) leaf_val.assign((size_t)C, 0.0);
     TCSDN_TRY(upload(&m->d_nodes, nodes.data(), nodes.size()));
     TCSDN_TRY(upload(&m->d_tree_base, tree_base.data(), tree_base.size()));
@@ -308,9 +328,8 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
 template <typename T>
 static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
     auto kern = forest_kernel<T>;
-    const int64_t fixed = (int64_t)m->d * kFRows * 4 + (int64_t)m->n_classes * kFRows * 8;
-    int64_t buf_nodes = m->n_groups == 1 && m->n_nodes <= m->group_node_cap ? m->n_nodes : m->group_node_cap;
-    if (m->max_group_nodes > 0 && m->n_groups > 1) buf_nodes = m->max_group_nodes;
+    const int64_t fixed = (int64_t)(m->d > m->n_classes ? m->d : m->n_classes) * kFRows * 4 + (int64_t)m->n_classes * kFRows * 8;
+    int64_t buf_nodes = (m->max_group_nodes > 0 ? m->max_group_nodes : 0) + 1;   // largest in-smem group + its halt node
     if (buf_nodes < 64) buf_nodes = 64;
     const size_t smem = (size_t)fixed + (size_t)buf_nodes * 8;
     TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
