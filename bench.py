@@ -36,6 +36,17 @@ WORKLOADS = ("gnb", "logistic", "kmeans", "forest", "forest_hbm", "knn", "svc")
 
 # ----------------------------------------------------------------------------- workload definitions
 def build_workload(name, quick=False):
+    w = _build_workload(name, quick)
+    w["name"] = name
+    w["full_rows"] = _FULL_ROWS[name]
+    return w
+
+
+_FULL_ROWS = {"gnb": 1_000_000, "logistic": 10_000_000, "kmeans": 10_000_000, "forest": 12_500_000, "forest_hbm": 2_000_000,
+              "knn": 10_000_000, "svc": 10_000_000}
+
+
+def _build_workload(name, quick=False):
     """-> dict(spec, d, rows (per GPU per step), bytes_per_row, flops_per_row, desc, cpu_sample_rows)"""
     from traffic_classifier_sdn_b200 import synth
     from traffic_classifier_sdn_b200.modelio import spec_from_estimator
@@ -280,11 +291,16 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     else:
         achieved = rows * w["flops_per_row"] / (kernel_ms * 1e-3) / 1e12
         unit = "TFLOP/s"
-    return dict(value=value, ms_per_step=ms / steps, kernel_ms=kernel_ms, rows=rows, ring=ring, mode=mode,
+    tr = load_traffic(w["name"])
+    if tr is not None:
+        # the capture was taken on the full-size workload; scale if this run uses another batch size (--quick)
+        tr = dict(tr, bytes=tr["bytes"] * rows / w["full_rows"])
+    return dict(value=value, ms_per_step=ms / steps, kernel_ms=kernel_ms, rows=rows, ring=ring, mode=mode, traffic=tr,
                 launches_per_step=launches_per_step, load_window=load_window,
                 e2e=dict(value=e2e, unit="flow-rows/s", h2d_bytes_per_step=rows * row_bytes, d2h_bytes_per_step=rows * 4),
                 roofline=dict(bound=w["bound"], achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
-                              traffic=None, peak_source=peaks["source"]),
+                              traffic=None if tr is None else tr["bytes"], traffic_source=None if tr is None else tr["source"],
+                              peak_source=peaks["source"]),
                 est=est, batch0=batches[0])
 
 
@@ -316,6 +332,19 @@ def cpu_reference(w, max_seconds=20.0, threads=None):
     return dict(value=n / best, unit="flow-rows/s", cores=cores, kind="reference",
                 sample=f"sklearn {type(sk).__name__}.predict on {n} of the workload's rows, best of 2, "
                        f"{cores} host threads available (n_jobs=-1 where the estimator has it)")
+
+
+def load_traffic(name):
+    """DRAM bytes per launch of the workload's dominant kernel, from the committed ncu capture (profiles/)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for f in sorted(os.listdir(pdir)):
+            if f.endswith("_ncu_summary.json"):
+                j = json.load(open(os.path.join(pdir, f)))
+                if name in j and j[name].get("dram_bytes"):
+                    best = {"bytes": j[name]["dram_bytes"], "source": f"profiles/{f}"}
+    return best
 
 
 def load_peaks():

@@ -1,0 +1,53 @@
+"""Row-sharded data parallelism over the GPUs of one box.
+
+Rows are independent and the models are tiny, so the path shards by rows only: rank r of W classifies the
+contiguous block [r*ceil(n/W), (r+1)*ceil(n/W)) with its own replica of the model, and there is NO collective
+on the data path.  The only exchange the reference's use could want is the full label vector on every rank:
+one all-gather of int32 class indices (NCCL over NVLink when the tensors are CUDA tensors, gloo on CPU).
+
+One process per GPU (torchrun); ``torch.distributed`` is plumbing, the kernels never see it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous block of rank `rank`: (start, stop).  Blocks differ by at most ceil-rounding; empty blocks allowed."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    per = -(-n // world)
+    start = min(n, rank * per)
+    return start, min(n, start + per)
+
+
+def predict_sharded(model, X, gather: bool = True, group=None):
+    """Classify this rank's block of X (every rank holds the same X, or at least its own block's rows).
+
+    Returns the int32 class indices of the whole batch on every rank when ``gather`` (one all-gather of the
+    per-rank label vectors, padded to equal length), else only this rank's block.  Works with numpy arrays
+    (gloo) and CUDA tensors (NCCL)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return model.predict_indices(X)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = len(X)
+    a, b = shard_bounds(n, rank, world)
+    local = model.predict_indices(X[a:b]) if b > a else (X.new_empty(0, dtype=torch.int32) if torch.is_tensor(X)
+                                                         else np.empty(0, np.int32))
+    if not gather:
+        return local
+    per = -(-n // world)
+    is_t = torch.is_tensor(local)
+    t = local if is_t else torch.from_numpy(np.ascontiguousarray(local))
+    pad = torch.zeros(per, dtype=torch.int32, device=t.device)   # equal-sized contributions for the collective
+    pad[: t.numel()] = t
+    out = torch.empty(per * world, dtype=torch.int32, device=t.device)
+    if t.is_cuda:
+        dist.all_gather_into_tensor(out, pad, group=group)
+    else:
+        dist.all_gather(list(out.split(per)), pad, group=group)
+    # blocks are contiguous and only the trailing ranks can be short, so dropping the tail removes all padding
+    res = out[:n]
+    return res if is_t else res.numpy()
