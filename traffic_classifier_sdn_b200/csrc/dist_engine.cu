@@ -15,8 +15,13 @@
 // acc <= (worst kept distance - ||x||^2) + kappa (||x||^2 + ||t||^2), kappa = 2^-18; every row the sequential heap
 // would accept passes, every row that passes goes through the same heap_push in index order -> neighbours
 // identical to knn.cu / sklearn.  (The kappa ||t||^2 part is folded into the packed norm: B carries (1-kappa)||t||^2.)
-// SVC uses acc directly: e = -gamma log2(e) (acc + ||x||^2), K = ex2(e), C-1 fp32 FMAs per pair into the running
-// sums of the support vector's class, tile sums promoted to fp64 (tolerance: tests/test_engine_gpu.py).
+// SVC uses acc directly: e = -gamma log2(e) (acc + ||x - c_j||^2), K = ex2(e), C-1 fp32 FMAs per pair into the running
+// sums of the support vector's class, tile sums promoted to fp64 (tolerance: tests/test_engine_gpu.py).  To keep the
+// fp32 accumulation error small where K is not negligible, support vectors are re-ordered inside their class into
+// spatially compact tiles and every tile is expanded around ITS OWN centre c_j: B holds u = s - c_j, three extra K
+// slots hold the scalar 2 (c_j - c0).u, so the (globally centred) A operand effectively becomes x - c_j, and the
+// epilogue adds ||x - c_j||^2 computed directly in fp32.  The error is then 2^-21 (|x - c_j| r_j) instead of
+// 2^-21 (||x||^2 + ||s||^2).
 //
 // Data layout.  create() packs the reference rows once into tile images of 64 rows x K=80 bf16 in the UMMA
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
@@ -57,7 +62,7 @@ constexpr int kERows = 512;          // query rows per CTA pass (4 MMA tiles of 
 constexpr int kEN = 64;              // reference rows per tile (MMA N)
 constexpr int kEK = 80;              // packed K
 constexpr int kEKSteps = kEK / 16;
-constexpr int kEMaxD = 12;           // 6 d + 3 <= 80
+constexpr int kEMaxD = 12;           // 6 d + 6 <= 80
 constexpr int kEStages = 4;
 constexpr int kETileB = kEN * kEK * 2;      // 10240 bytes of bf16 per reference tile
 constexpr int kEATile = 128 * kEK * 2;      // 20480 bytes per query tile
@@ -156,6 +161,22 @@ __device__ __forceinline__ void e_tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 16-column TMEM load split into "issue" and "wait", so that the next chunk can be in flight while the current one is
+// processed.  The wait names the registers as in/out operands: the compiler must not touch them before it.
+__device__ __forceinline__ void e_tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void e_tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ float e_ex2(float x) {   // one MUFU.EX2 (2 ulp), flushes denormals
     float y;
@@ -334,6 +355,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 }
                 const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
                 pk[6 * A.d + 0] = one; pk[6 * A.d + 1] = one; pk[6 * A.d + 2] = one;
+                if (SVC) { pk[6 * A.d + 3] = one; pk[6 * A.d + 4] = one; pk[6 * A.d + 5] = one; }   // 2 (c_j - c0).u slots
                 unsigned char *dst = sA + qt * kEATile + (rt >> 3) * kESBO + (rt & 7) * 16;
 #pragma unroll
                 for (int c = 0; c < kEK / 8; ++c)
@@ -440,8 +462,14 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 }
             } else {
                 // ================================================================ SVC: exp + one-vs-one sums
-                const float bias = A.g2 * (float)qn;                 // e = g2 * (acc + ||x||^2)
+                // Every support-vector tile carries its own centre c_j (tiles are spatially compact, see create()):
+                //   acc = ||u||^2 - 2 (x - c_j).u,  u = s - c_j      (B holds u and the scalar 2 (c_j - c0).u per row)
+                //   d   = ||x - c_j||^2 + acc ,  ||x - c_j||^2 summed directly in fp32 (no cancellation)
+                // so the fp32 accumulation error scales with |x - c_j| r_j instead of ||x||^2 + ||s||^2.
                 const float g2 = A.g2;
+                float x32[kEMaxD];
+#pragma unroll
+                for (int j = 0; j < kEMaxD; ++j) x32[j] = (float)q[j];
                 float tsum[NC1];
                 double csum[NC1];
                 double S[(NC1 + 1) * NC1];                            // S[i][m] = sum_{s in class i} coef[m][s] K_s (local memory)
@@ -460,30 +488,36 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     }
                     e_mbar_wait(&accFull[b], bph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // the coefficients were written by the bulk copy (async proxy): observe ITS barrier before reading them
-                    // (already complete here -- the MMAs consumed the same stage -- so this never blocks)
+                    const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
+                    uint32_t va[16], vb[16];
+                    e_tmem_ld16_issue(taddr, va);
+                    // the coefficients and the tile centre were written by the bulk copy (async proxy): observe ITS barrier
+                    // before reading them (already complete here -- the MMAs consumed the same stage -- so this never blocks)
                     e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
                     const float *coef = reinterpret_cast<const float *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
-                    const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
+                    const float4 *ctr = reinterpret_cast<const float4 *>(coef + NC1 * kEN);
+                    float xn = 0.f;   // ||x - c_j||^2 summed directly in fp32: relative error 1e-7 of itself
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float v[32];
-                        e_tmem_ld32(taddr + h * 32, v);
-                        if (h == 1) {
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) e_mbar_arrive(&accEmpty[b]);
-                        }
+                    for (int j4 = 0; j4 < kEMaxD / 4; ++j4) {
+                        const float4 c = ctr[j4];
+                        float t;
+                        t = x32[j4 * 4 + 0] - c.x; xn = fmaf(t, t, xn);
+                        t = x32[j4 * 4 + 1] - c.y; xn = fmaf(t, t, xn);
+                        t = x32[j4 * 4 + 2] - c.z; xn = fmaf(t, t, xn);
+                        t = x32[j4 * 4 + 3] - c.w; xn = fmaf(t, t, xn);
+                    }
+                    const float bias = g2 * xn;                        // e = g2 * (acc + ||x - c_j||^2)
+                    auto chunk = [&](const uint32_t (&v)[16], int col0) {
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
+                        for (int c4 = 0; c4 < 4; ++c4) {
                             float4 cf[NC1];
 #pragma unroll
                             for (int m = 0; m < NC1; ++m)
-                                cf[m] = *reinterpret_cast<const float4 *>(coef + m * kEN + h * 32 + c4 * 4);
-                            const float k0 = e_ex2(fmaf(v[c4 * 4 + 0], g2, bias));
-                            const float k1 = e_ex2(fmaf(v[c4 * 4 + 1], g2, bias));
-                            const float k2 = e_ex2(fmaf(v[c4 * 4 + 2], g2, bias));
-                            const float k3 = e_ex2(fmaf(v[c4 * 4 + 3], g2, bias));
+                                cf[m] = *reinterpret_cast<const float4 *>(coef + m * kEN + col0 + c4 * 4);
+                            const float k0 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 0]), g2, bias));
+                            const float k1 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 1]), g2, bias));
+                            const float k2 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 2]), g2, bias));
+                            const float k3 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 3]), g2, bias));
 #pragma unroll
                             for (int m = 0; m < NC1; ++m) {
                                 tsum[m] = fmaf(cf[m].x, k0, tsum[m]);
@@ -492,16 +526,24 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                                 tsum[m] = fmaf(cf[m].w, k3, tsum[m]);
                             }
                         }
-                    }
+                    };
+                    e_tmem_ld16_wait(va); e_tmem_ld16_issue(taddr + 16, vb); chunk(va, 0);
+                    e_tmem_ld16_wait(vb); e_tmem_ld16_issue(taddr + 32, va); chunk(vb, 16);
+                    e_tmem_ld16_wait(va); e_tmem_ld16_issue(taddr + 48, vb); chunk(va, 32);
+                    e_tmem_ld16_wait(vb);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) e_mbar_arrive(&accEmpty[b]);        // TMEM buffer may be overwritten
+                    chunk(vb, 48);
                     // Release the stage only after every coefficient load has actually been PERFORMED: mbarrier.arrive does
                     // not wait for outstanding ld.shared (see the file header).  The barrier address is made data-dependent
                     // on the accumulators that consumed every coefficient, so the arrive cannot issue before the loads return
-                    // (cheaper than a MEMBAR.CTA per tile: that one costs ~10 % of the epilogue).
+                    // (cheaper than a MEMBAR.CTA per tile).
                     {
-                        float dep = 0.f;
+                        float dep = xn;
 #pragma unroll
                         for (int m = 0; m < NC1; ++m) dep += tsum[m];
-                        const uint32_t off = (dep == 1.2345e38f) ? 8u : 0u;   // never true for finite sums of |coef| <= C
+                        const uint32_t off = (dep == 1.2345e38f) ? 8u : 0u;   // never true for finite sums
                         __syncwarp();
                         if (lane == 0)
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
@@ -538,12 +580,17 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static void pack_row(unsigned char *tile, int r, const double *x, const double *center, int d, double norm_scale) {
-    double nrm = 0.0;
+// One reference row into row r of a tile image.  `center` is what the B operand is centred on; `delta` (SVC) is
+// (tile centre - global centre): the scalar 2 delta.u rides in three extra K slots against A's 1.0, which turns the
+// globally centred A operand into a locally centred one: ||u||^2 + 2 delta.u - 2 (x - c0).u = ||u||^2 - 2 (x - c_j).u
+static void pack_row(unsigned char *tile, int r, const double *x, const double *center, const double *delta, int d,
+                     double norm_scale) {
+    double nrm = 0.0, w = 0.0;
     float c32[kEMaxD];
     for (int j = 0; j < d; ++j) {
         c32[j] = static_cast<float>(x[j] - center[j]);
         nrm += (double)c32[j] * (double)c32[j];
+        if (delta) w += 2.0 * delta[j] * (double)c32[j];
     }
     auto put = [&](int k, __nv_bfloat16 v) { memcpy(tile + tile_off(r, k), &v, 2); };
     for (int j = 0; j < d; ++j) {
@@ -555,6 +602,29 @@ static void pack_row(unsigned char *tile, int r, const double *x, const double *
     __nv_bfloat16 h, m, l;
     split3(static_cast<float>(nrm * norm_scale), h, m, l);   // KNN folds the filter slack in: (1 - kappa) ||t||^2
     put(6 * d + 0, h); put(6 * d + 1, m); put(6 * d + 2, l);
+    if (delta) {
+        split3(static_cast<float>(w), h, m, l);
+        put(6 * d + 3, h); put(6 * d + 4, m); put(6 * d + 5, l);
+    }
+}
+
+// kd-style ordering: recursively split on the widest coordinate at the median until <= 64 rows remain, emit leaves in
+// order.  Consecutive runs of 64 in this order are spatially compact, which is all the SVC tiles need.
+static void compact_order(const std::vector<double> &ref, int d, std::vector<int32_t> &idx, size_t lo, size_t hi) {
+    if (hi - lo <= (size_t)kEN) return;
+    int best = 0;
+    double bw = -1.0;
+    for (int j = 0; j < d; ++j) {
+        double mn = 1e300, mx = -1e300;
+        for (size_t i = lo; i < hi; ++i) { const double v = ref[(size_t)idx[i] * d + j]; mn = std::min(mn, v); mx = std::max(mx, v); }
+        if (mx - mn > bw) { bw = mx - mn; best = j; }
+    }
+    size_t mid = lo + (((hi - lo) / 2 + kEN - 1) / kEN) * kEN;   // split at a tile boundary
+    if (mid >= hi) mid = lo + (hi - lo) / 2;
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                     [&](int32_t a, int32_t b2) { return ref[(size_t)a * d + best] < ref[(size_t)b2 * d + best]; });
+    compact_order(ref, d, idx, lo, mid);
+    compact_order(ref, d, idx, mid, hi);
 }
 
 static void pack_dummy(unsigned char *tile, int r, int d) {  // a row that is "infinitely" far from everything
@@ -585,18 +655,23 @@ int engine_create(tcsdn_model *m) {
     EngineState *E = new EngineState();
     const int nc1 = svc ? m->n_classes - 1 : 0;
     E->nc1 = nc1;
-    E->tile_bytes = kETileB + nc1 * kEN * (int)sizeof(float);
-    // tile plan: KNN = consecutive rows; SVC = per class, padded to a tile boundary
-    std::vector<int32_t> row0, rows, tclass;
+    E->tile_bytes = kETileB + nc1 * kEN * (int)sizeof(float) + (svc ? 16 * (int)sizeof(float) : 0);   // + tile centre (SVC)
+    // tile plan: KNN = consecutive rows in the original order (the heap semantics need index order);
+    // SVC = per class (sums are per class), rows re-ordered inside the class for spatial compactness (sums do not
+    // care about order), padded to a tile boundary with zero-coefficient rows
+    std::vector<int32_t> row0, rows, tclass, order((size_t)nref);
+    for (int64_t i = 0; i < nref; ++i) order[(size_t)i] = (int32_t)i;
     if (!svc) {
         for (int64_t r = 0; r < nref; r += kEN) { row0.push_back((int32_t)r); rows.push_back((int32_t)std::min<int64_t>(kEN, nref - r)); tclass.push_back(0); }
     } else {
         std::vector<int32_t> start(m->n_classes + 1);
         TCSDN_CUDA(cudaMemcpy(start.data(), m->d_start, start.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        for (int c = 0; c < m->n_classes; ++c)
+        for (int c = 0; c < m->n_classes; ++c) {
+            compact_order(ref, d, order, (size_t)start[c], (size_t)start[c + 1]);
             for (int r = start[c]; r < start[c + 1]; r += kEN) {
                 row0.push_back(r); rows.push_back(std::min(kEN, start[c + 1] - r)); tclass.push_back(c);
             }
+        }
     }
     E->n_tiles = (int)row0.size();
     std::vector<unsigned char> img((size_t)E->n_tiles * E->tile_bytes, 0);
@@ -607,12 +682,25 @@ int engine_create(tcsdn_model *m) {
     }
     for (int t = 0; t < E->n_tiles; ++t) {
         unsigned char *tile = img.data() + (size_t)t * E->tile_bytes;
+        double tc[kEMaxD], delta[kEMaxD];
+        if (svc) {   // tile centre: the mean of its rows, rounded to fp32 (the epilogue subtracts exactly this value)
+            for (int j = 0; j < d; ++j) {
+                double a = 0.0;
+                for (int r = 0; r < rows[t]; ++r) a += ref[(size_t)order[(size_t)(row0[t] + r)] * d + j];
+                tc[j] = (double)static_cast<float>(a / rows[t]);
+                delta[j] = tc[j] - center[j];
+            }
+            float *cp = reinterpret_cast<float *>(tile + kETileB + (size_t)nc1 * kEN * sizeof(float));
+            for (int j = 0; j < 16; ++j) cp[j] = j < d ? static_cast<float>(tc[j]) : 0.f;
+        }
         for (int r = 0; r < kEN; ++r) {
             if (r < rows[t]) {
-                pack_row(tile, r, &ref[(size_t)(row0[t] + r) * d], center.data(), d, svc ? 1.0 : 1.0 - (double)kKappa);
+                const int32_t src = order[(size_t)(row0[t] + r)];
+                pack_row(tile, r, &ref[(size_t)src * d], svc ? tc : center.data(), svc ? delta : nullptr, d,
+                         svc ? 1.0 : 1.0 - (double)kKappa);
                 if (svc) {
                     float *cf = reinterpret_cast<float *>(tile + kETileB);
-                    for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + row0[t] + r]);
+                    for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + src]);
                 }
             } else {
                 pack_dummy(tile, r, d);
