@@ -341,3 +341,40 @@ def test_flow_update_kernel_matches_host_formulas():
         torch.cuda.synchronize()
         assert np.array_equal(dstate.cpu().numpy(), host)
         assert np.array_equal(feats.cpu().numpy(), host[:, flows.FEATURE_COLUMNS])
+
+
+# ------------------------------------------------------------------ the CLI shim end to end (reference argv words)
+def test_cli_replays_a_monitor_log_through_the_gpu(tmp_path, golden, specs, capsys):
+    """`python -m ...cli gaussiannb --monitor-cmd 'cat log' --models DIR`: model files are read exactly like the reference
+    reads models/<Name> (pickles), the monitor's stdout lines are parsed like run_ryu does, every report classifies all
+    flows with one GPU predict.  (Ryu itself is not needed: the monitor command is replaced by a recorded log.)"""
+    import pickle
+    from sk_rebuild import sklearn_from_spec
+    from test_host import _monitor_log
+    from traffic_classifier_sdn_b200 import cli, flows, modelio
+    models = tmp_path / "models"
+    models.mkdir()
+    for word, fname in modelio.MODEL_FILES.items():
+        kind = {"logistic": "linear", "kmeans": "kmeans", "svm": "svc", "kneighbors": "knn", "Randomforest": "forest",
+                "gaussiannb": "gnb"}[word]
+        with open(models / fname, "wb") as fh:
+            pickle.dump(sklearn_from_spec(specs[kind], knn_algorithm="kd_tree"), fh)
+    log = tmp_path / "monitor.log"
+    lines = _monitor_log(np.random.default_rng(5), n_flows=7, polls=21)
+    log.write_bytes(b"".join(lines))
+    table = flows.FlowTable()
+    for ln in lines:
+        rec = flows.parse_monitor_line(ln)
+        if rec is not None:
+            table.ingest(rec)
+    for word in ("gaussiannb", "Randomforest", "kmeans", "knearest", "supervised", "svm"):
+        assert cli.main([word, "--monitor-cmd", f"cat {log}", "--models", str(models), "--every", "1"]) == 0
+        out = capsys.readouterr().out
+        assert out.count("Flow ID") >= 2 and "Traffic Type" in out
+        kind = {"gaussiannb": "gnb", "Randomforest": "forest", "kmeans": "kmeans", "knearest": "knn", "supervised": "linear",
+                "svm": "svc"}[word]
+        exp_idx = oracle.predict(specs[kind], table.features(), want_scores=False)[0]
+        exp = [cli.INT_LABELS[int(i)] if kind == "kmeans" else str(np.asarray(specs[kind]["classes"])[i]) for i in exp_idx]
+        final_table = out[out.rstrip().rfind("Flow ID"):]
+        got = [row.split("|")[4].strip() for row in final_table.splitlines() if row.startswith("|") and "Flow ID" not in row]
+        assert got == exp, (word, got, exp)   # --every 1: the last report is printed at the last data line = final state

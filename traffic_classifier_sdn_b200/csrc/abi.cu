@@ -18,7 +18,6 @@ void set_error(const char *fmt, ...) {
 }
 
 static int model_base(tcsdn_model **out, int kind, int d, int n_classes, int score_cols) {
-    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
     *out = nullptr;
     if (d <= 0 || d > 4096) { set_error("n_features=%d out of range", d); return TCSDN_EINVAL; }
     int count = 0;
@@ -181,6 +180,8 @@ static int scorer_common(tcsdn_model *m, const std::vector<double> &a, const std
 }
 
 int tcsdn_linear_create(const double *coef, const double *intercept, int32_t n_rows, int32_t d, tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!coef || !intercept || n_rows < 1 || n_rows > kMaxClasses) { set_error("linear: bad arguments"); return TCSDN_EINVAL; }
     if (!finite_all(coef, (size_t)n_rows * d) || !finite_all(intercept, n_rows)) { set_error("linear: non-finite parameter"); return TCSDN_EINVAL; }
     tcsdn_model *m;
@@ -194,6 +195,8 @@ int tcsdn_linear_create(const double *coef, const double *intercept, int32_t n_r
 
 int tcsdn_gnb_create(const double *theta, const double *var, const double *class_prior, int32_t n_classes, int32_t d,
                      tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!theta || !var || !class_prior || n_classes < 1 || n_classes > kMaxClasses) { set_error("gnb: bad arguments"); return TCSDN_EINVAL; }
     for (size_t i = 0; i < (size_t)n_classes * d; ++i)
         if (!(var[i] > 0.0) || !std::isfinite(var[i]) || !std::isfinite(theta[i])) { set_error("gnb: var_ must be finite and > 0"); return TCSDN_EINVAL; }
@@ -218,6 +221,8 @@ int tcsdn_gnb_create(const double *theta, const double *var, const double *class
 }
 
 int tcsdn_kmeans_create(const double *centers, int32_t k, int32_t d, tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!centers || k < 1 || k > kMaxClasses) { set_error("kmeans: bad arguments (k <= %d)", kMaxClasses); return TCSDN_EINVAL; }
     if (!finite_all(centers, (size_t)k * d)) { set_error("kmeans: non-finite center"); return TCSDN_EINVAL; }
     tcsdn_model *m;
@@ -241,6 +246,8 @@ int tcsdn_kmeans_create(const double *centers, int32_t k, int32_t d, tcsdn_model
 
 int tcsdn_knn_create(const double *fit_x, const int32_t *y, int64_t n_train, int32_t d, int32_t n_classes, int32_t k,
                      tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!fit_x || !y || n_train < 1 || n_classes < 1 || n_classes > 256) { set_error("knn: bad arguments"); return TCSDN_EINVAL; }
     if (k < 1 || k > 64 || k > n_train) { set_error("knn: need 1 <= k <= min(64, n_train), got k=%d n_train=%lld", k, (long long)n_train); return TCSDN_EINVAL; }
     if (n_train > (int64_t)INT32_MAX) { set_error("knn: n_train too large"); return TCSDN_EINVAL; }
@@ -260,6 +267,8 @@ int tcsdn_knn_create(const double *fit_x, const int32_t *y, int64_t n_train, int
 
 int tcsdn_svc_create(const double *sv, const double *dual_coef, const double *intercept, const int32_t *n_support,
                      int32_t n_sv, int32_t d, int32_t n_classes, double gamma, tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!sv || !dual_coef || !intercept || !n_support || n_sv < 1 || n_classes < 2 || n_classes > 16) {
         set_error("svc: bad arguments (2 <= n_classes <= 16)");
         return TCSDN_EINVAL;
@@ -294,6 +303,8 @@ int tcsdn_svc_create(const double *sv, const double *dual_coef, const double *in
 int tcsdn_forest_create(const int64_t *tree_offsets, const int32_t *left, const int32_t *right, const int32_t *feature,
                         const double *threshold, const double *value, int32_t n_trees, int32_t d, int32_t n_classes,
                         tcsdn_model_t **out) {
+    if (!out) { set_error("out handle pointer is NULL"); return TCSDN_EINVAL; }
+    *out = nullptr;
     if (!tree_offsets || !left || !right || !feature || !threshold || !value || n_trees < 1 || n_classes < 1) {
         set_error("forest: bad arguments");
         return TCSDN_EINVAL;

@@ -104,7 +104,6 @@ struct tcsdn_model {
     int64_t n_nodes = 0;
     int group_node_cap = 0;          // nodes that fit in the smem tree buffer
     int max_group_nodes = 0;
-    bool forest_all_smem = false;    // every group fits in shared memory
 
     // ---- per-handle misc
     int32_t *d_flag = nullptr;       // device error flag (non-finite input)

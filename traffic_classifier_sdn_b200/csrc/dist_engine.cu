@@ -25,7 +25,8 @@
 //
 // Data layout.  create() packs the reference rows once into tile images of 64 rows x K=80 bf16 in the UMMA
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
-// followed (SVC) by the tile's dual coefficients [C-1][64] fp32.  A tile image is contiguous in HBM, so one
+// followed by side data the epilogue needs: SVC the tile's dual coefficients [C-1][64] fp32 and centre, KNN the tile's
+// original fp64 rows (exact re-evaluation reads them from shared memory, not from L2).  A tile image is contiguous in HBM, so one
 // cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
 // boundaries (padded with zero-coefficient rows).
 //
@@ -205,32 +206,29 @@ __host__ __device__ __forceinline__ size_t tile_off(int row, int k) {  // byte o
 }
 
 // ------------------------------------------------------------------------------------------------ KNN heap
-struct KnnState {
-    double hv[kEMaxK];
-    int32_t hi[kEMaxK];
-    float thr_base;      // (worst kept distance - ||x||^2) + kappa ||x||^2, rounded up
-};
+constexpr int kEHeapSmemK = 8;   // heaps of k <= 8 neighbours live in shared memory ([slot][thread]); larger k in local memory
 
+// sk:utils/_heap.pyx:6-88 (the caller has checked val < root).  Slot i of the heap lives at values[i * ST]: ST = 1 for a
+// thread-private array, ST = 512 for the shared-memory layout [slot][thread] (conflict-free across a warp).
+template <int ST>
 __device__ __forceinline__ void knn_heap_push(double *values, int32_t *indices, int size, double val, int32_t val_idx) {
-    values[0] = val;     // sk:utils/_heap.pyx:6-88 (caller has checked val < values[0])
-    indices[0] = val_idx;
     int cur = 0;
     for (;;) {
         int l = 2 * cur + 1, r = l + 1, swap;
         if (l >= size) break;
         if (r >= size) {
-            if (values[l] > val) swap = l; else break;
-        } else if (values[l] >= values[r]) {
-            if (val < values[l]) swap = l; else break;
+            if (values[l * ST] > val) swap = l; else break;
         } else {
-            if (val < values[r]) swap = r; else break;
+            const double vl = values[l * ST], vr = values[r * ST];
+            if (vl >= vr) { if (val < vl) swap = l; else break; }
+            else          { if (val < vr) swap = r; else break; }
         }
-        values[cur] = values[swap];
-        indices[cur] = indices[swap];
+        values[cur * ST] = values[swap * ST];
+        indices[cur * ST] = indices[swap * ST];
         cur = swap;
     }
-    values[cur] = val;
-    indices[cur] = val_idx;
+    values[cur * ST] = val;
+    indices[cur * ST] = val_idx;
 }
 
 __device__ __forceinline__ float knn_thr_base(double hv0, double qn) {
@@ -249,7 +247,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kEStages * A.tile_bytes);
     uint64_t *fullB = bars, *emptyB = bars + kEStages, *accFull = bars + 2 * kEStages, *accEmpty = accFull + 2;
     uint64_t *aFull = accEmpty + 2;
-    uint64_t *coefFree = aFull + 1;      // SVC: the 16 epilogue warps are done with a stage's coefficients
+    uint64_t *coefFree = aFull + 1;      // the 16 epilogue warps are done with a stage's side data (SVC coefficients, KNN fp64 rows)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(coefFree + kEStages);
     unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + 256;   // KNN: [512 threads][kEListCap] column indices
 
@@ -260,7 +258,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
         for (int s = 0; s < kEStages; ++s) {
             e_mbar_init(&fullB[s], 1);
             e_mbar_init(&emptyB[s], 1);      // tcgen05.commit: the MMAs have read the stage
-            e_mbar_init(&coefFree[s], 16);   // SVC: every epilogue warp has read the stage's coefficients
+            e_mbar_init(&coefFree[s], 16);   // every epilogue warp has read the stage's side data
         }
         for (int b = 0; b < 2; ++b) {
             e_mbar_init(&accFull[b], 1);
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 for (int j = 0; j < A.n_tiles; ++j, ++g) {
                     const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
                     e_mbar_wait(&emptyB[s], ph ^ 1);
-                    if (SVC) e_mbar_wait(&coefFree[s], ph ^ 1);
+                    e_mbar_wait(&coefFree[s], ph ^ 1);   // the epilogue warps are done with the stage's side data
                     e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
                     e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)j * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
                 }
@@ -370,13 +368,24 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 // acc = (1 - kappa) ||t||^2 - 2 x.t, so a row passes iff acc <= thr = (worst kept distance - ||x||^2)
                 // + kappa ||x||^2.  Passing columns are listed per thread, then every lane walks its own list: exact
                 // fp64 distance (sklearn's rdist order) + heap_push, in column = training-index order.
-                KnnState s;
-                for (int i = 0; i < A.k; ++i) { s.hv[i] = DBL_MAX; s.hi[i] = 0; }
-                s.thr_base = FLT_MAX;
+                // The k-slot max-heap: shared memory [slot][thread] for k <= 8 (template NC1 == 1), else thread-private local
+                // memory (NC1 == 2).  Its root and the filter threshold stay in registers: the common "candidate is not
+                // better than the worst kept one" test touches no memory.
+                constexpr bool kHeapSmem = (NC1 == 1);
+                constexpr int ST = kHeapSmem ? 512 : 1;
+                double hv_local[kHeapSmem ? 1 : kEMaxK];
+                int32_t hi_local[kHeapSmem ? 1 : kEMaxK];
+                double *hv = kHeapSmem ? reinterpret_cast<double *>(cand + 512 * kEListCap) + tid : hv_local;
+                int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(cand + 512 * kEListCap + 512 * kEHeapSmemK * 8) + tid : hi_local;
+                for (int i = 0; i < A.k; ++i) { hv[i * ST] = DBL_MAX; hi[i * ST] = 0; }
+                double hv0 = DBL_MAX;
+                float thr_base = FLT_MAX;
                 unsigned long long n_exact = 0;
                 unsigned char *mylist = cand + (size_t)tid * kEListCap;
                 const bool audit = A.maxratio != nullptr;
+                float dep = 0.f;   // consumes every shared-memory load of the candidate loop (see the stage release below)
                 for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                    const uint32_t sidx = g % kEStages;
                     const uint32_t b = g & 1, bph = (g >> 1) & 1;
                     e_mbar_wait(&accFull[b], bph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
-                    const float thr = !live ? -FLT_MAX : (audit ? FLT_MAX : s.thr_base);
+                    const float thr = !live ? -FLT_MAX : (audit ? FLT_MAX : thr_base);
                     // group minima first: the common case is "nothing in this group of 8 passes"
                     uint32_t gmask = 0;
 #pragma unroll
@@ -402,6 +411,10 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                         if (e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7])) <= thr) gmask |= 1u << gq;
                     }
                     if (__any_sync(0xffffffffu, gmask != 0)) {
+                        // the tile's original fp64 rows ride behind the bf16 image in the same ring stage (written by the bulk
+                        // copy: observe its barrier first; complete long ago, never blocks)
+                        e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
+                        const double *trows = reinterpret_cast<const double *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
                         const int nreal = A.tile_rows[j];
                         int cnt = 0;
 #pragma unroll
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                             if (i < cnt) {
                                 const int c = mylist[i];
                                 const int32_t idx = row0 + c;
-                                const double *t = A.ref + (size_t)idx * A.d;
+                                const double *t = trows + c * A.d;
                                 double dist = 0.0;
 #pragma unroll
                                 for (int jj = 0; jj < kEMaxD; ++jj)
@@ -441,19 +454,30 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                                     atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
                                 }
                                 ++n_exact;
-                                if (dist < s.hv[0]) {
-                                    knn_heap_push(s.hv, s.hi, A.k, dist, idx);
-                                    s.thr_base = knn_thr_base(s.hv[0], qn);
+                                dep += (float)dist;
+                                if (dist < hv0) {
+                                    knn_heap_push<ST>(hv, hi, A.k, dist, idx);
+                                    hv0 = hv[0];
+                                    thr_base = knn_thr_base(hv0, qn);
                                 }
                             }
                         }
+                    }
+                    // release the stage: the barrier address depends on every value loaded from it (mbarrier.arrive does not
+                    // wait for outstanding ld.shared, see the file header)
+                    {
+                        // the candidate loads run under divergence, so lane 0 must depend on EVERY lane's loads: a warp vote
+                        const uint32_t off = __any_sync(0xffffffffu, dep == -1.0f) ? 8u : 0u;   // never true: dep sums squared distances
+                        __syncwarp();
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
                     }
                 }
                 if (live) {
                     int best = 0, arg = 0;
                     for (int c = 0; c < A.C; ++c) {
                         int cnt = 0;
-                        for (int i = 0; i < A.k; ++i) cnt += (A.y[s.hi[i]] == c);
+                        for (int i = 0; i < A.k; ++i) cnt += (A.y[hi[i * ST]] == c);
                         if (scores) scores[row * A.C + c] = (double)cnt / (double)A.k;
                         if (cnt > best) { best = cnt; arg = c; }
                     }
@@ -655,7 +679,9 @@ int engine_create(tcsdn_model *m) {
     EngineState *E = new EngineState();
     const int nc1 = svc ? m->n_classes - 1 : 0;
     E->nc1 = nc1;
-    E->tile_bytes = kETileB + nc1 * kEN * (int)sizeof(float) + (svc ? 16 * (int)sizeof(float) : 0);   // + tile centre (SVC)
+    // tile image = bf16 B operand, then SVC: dual coefficients + tile centre; KNN: the tile's original fp64 rows
+    E->tile_bytes = kETileB + (svc ? nc1 * kEN * (int)sizeof(float) + 16 * (int)sizeof(float)
+                                   : ((kEN * d * (int)sizeof(double) + 15) / 16) * 16);
     // tile plan: KNN = consecutive rows in the original order (the heap semantics need index order);
     // SVC = per class (sums are per class), rows re-ordered inside the class for spatial compactness (sums do not
     // care about order), padded to a tile boundary with zero-coefficient rows
@@ -701,6 +727,8 @@ int engine_create(tcsdn_model *m) {
                 if (svc) {
                     float *cf = reinterpret_cast<float *>(tile + kETileB);
                     for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + src]);
+                } else {
+                    memcpy(tile + kETileB + (size_t)r * d * sizeof(double), &ref[(size_t)src * d], (size_t)d * sizeof(double));
                 }
             } else {
                 pack_dummy(tile, r, d);
@@ -749,7 +777,9 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     A.flag = m->opt_check_finite ? m->d_flag : nullptr; A.n = n; A.n_tiles = E->n_tiles;
     A.tile_bytes = E->tile_bytes; A.d = m->d; A.k = m->k; A.C = m->n_classes; A.nc1 = E->nc1;
     A.g2 = static_cast<float>(-m->gamma * 1.4426950408889634);
-    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 + (svc ? 0 : 512 * (size_t)kEListCap);
+    const bool heap_smem = !svc && m->k <= kEHeapSmemK;
+    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 + (svc ? 0 : 512 * (size_t)kEListCap) +
+                        (heap_smem ? 512 * (size_t)kEHeapSmemK * 12 : 0);
     const int64_t n_super = (n + kERows - 1) / kERows;
     const unsigned grid = (unsigned)std::min<int64_t>(n_super, m->sm_count);
 #define TCSDN_LAUNCH(SVCF, NC)                                                                                    \
@@ -758,7 +788,7 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
         TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         kern<<<grid, kEThreads, smem, st>>>(A, x, labels, scores, E->d_counters);                                 \
     }
-    if (!svc) TCSDN_LAUNCH(false, 1)
+    if (!svc) { if (heap_smem) TCSDN_LAUNCH(false, 1) else TCSDN_LAUNCH(false, 2) }
     else switch (E->nc1) {
         case 1: TCSDN_LAUNCH(true, 1) break;
         case 2: TCSDN_LAUNCH(true, 2) break;
