@@ -184,6 +184,14 @@ __device__ __forceinline__ float e_ex2(float x) {   // one MUFU.EX2 (2 ulp), flu
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32 FMA (FFMA2): acc.{x,y} += a.{x,y} * b.{x,y} in ONE issue slot
+__device__ __forceinline__ void e_fma2(float2 &acc, const float2 a, const float2 b) {
+    unsigned long long d = *reinterpret_cast<unsigned long long *>(&acc);
+    const unsigned long long ua = *reinterpret_cast<const unsigned long long *>(&a);
+    const unsigned long long ub = *reinterpret_cast<const unsigned long long *>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(ua), "l"(ub));
+    acc = *reinterpret_cast<float2 *>(&d);
+}
 __device__ __forceinline__ float e_min3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
@@ -371,7 +379,8 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 // The k-slot max-heap: shared memory [slot][thread] for k <= 8 (template NC1 == 1), else thread-private local
                 // memory (NC1 == 2).  Its root and the filter threshold stay in registers: the common "candidate is not
                 // better than the worst kept one" test touches no memory.
-                constexpr bool kHeapSmem = (NC1 == 1);
+                constexpr bool kHeapSmem = (NC1 & 1) != 0;      // KNN instantiations: NC1 bit 0 = heap in shared memory,
+                constexpr bool kAudit = (NC1 & 2) != 0;         //                     bit 1 = audit mode (error statistic)
                 constexpr int ST = kHeapSmem ? 512 : 1;
                 double hv_local[kHeapSmem ? 1 : kEMaxK];
                 int32_t hi_local[kHeapSmem ? 1 : kEMaxK];
@@ -382,51 +391,64 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 float thr_base = FLT_MAX;
                 unsigned long long n_exact = 0;
                 unsigned char *mylist = cand + (size_t)tid * kEListCap;
-                const bool audit = A.maxratio != nullptr;
+                constexpr bool audit = kAudit;
                 float dep = 0.f;   // consumes every shared-memory load of the candidate loop (see the stage release below)
                 for (int j = 0; j < A.n_tiles; ++j, ++g) {
                     const uint32_t sidx = g % kEStages;
                     const uint32_t b = g & 1, bph = (g >> 1) & 1;
                     e_mbar_wait(&accFull[b], bph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    float v[64];
-                    {
-                        float lo[32], hi[32];
-                        const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
-                        e_tmem_ld32(taddr, lo);
-                        e_tmem_ld32(taddr + 32, hi);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
                     const float thr = !live ? -FLT_MAX : (audit ? FLT_MAX : thr_base);
-                    // group minima first: the common case is "nothing in this group of 8 passes"
-                    uint32_t gmask = 0;
+                    const int nreal = A.tile_rows[j];
+                    int cnt = 0;
+                    // two halves of 32 columns (keeps 32, not 64, accumulator values live): group minima first -- the common
+                    // case is "nothing in this group of 8 passes" -- then the passing columns are listed
 #pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        const float m0 = e_min3(v[gq * 8 + 0], v[gq * 8 + 1], v[gq * 8 + 2]);
-                        const float m1 = e_min3(v[gq * 8 + 3], v[gq * 8 + 4], v[gq * 8 + 5]);
-                        if (e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7])) <= thr) gmask |= 1u << gq;
+                    for (int h = 0; h < 2; ++h) {
+                        float v[32];
+                        e_tmem_ld32(tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN + h * 32), v);
+                        if (h == 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
+                        }
+                        uint32_t gmask = 0;
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            const float m0 = e_min3(v[gq * 8 + 0], v[gq * 8 + 1], v[gq * 8 + 2]);
+                            const float m1 = e_min3(v[gq * 8 + 3], v[gq * 8 + 4], v[gq * 8 + 5]);
+                            if (e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7])) <= thr) gmask |= 1u << gq;
+                        }
+                        if (__any_sync(0xffffffffu, gmask != 0)) {
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                if (!__any_sync(0xffffffffu, (gmask >> gq) & 1u)) continue;
+#pragma unroll
+                                for (int c = gq * 8; c < gq * 8 + 8; ++c) {
+                                    const bool pass = ((gmask >> gq) & 1u) && v[c] <= thr && (h * 32 + c) < nreal;
+                                    if (pass) mylist[cnt] = (unsigned char)(h * 32 + c);
+                                    cnt += pass;
+                                    if constexpr (kAudit) {   // error statistic while the accumulator value is at hand
+                                        if (pass) {
+                                            const double *t = A.ref + (size_t)(A.tile_row0[j] + h * 32 + c) * A.d;
+                                            double dist = 0.0, tn = 0.0;
+                                            for (int jj = 0; jj < A.d; ++jj) {
+                                                const double df = q[jj] - t[jj], u = t[jj] - A.center[jj];
+                                                dist += df * df; tn += u * u;
+                                            }
+                                            const float ratio = (float)(fabs((double)v[c] - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
+                                            atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
+                                        }
+                                    }
+                                }
+                            }
+                        }
                     }
-                    if (__any_sync(0xffffffffu, gmask != 0)) {
+                    if (__any_sync(0xffffffffu, cnt != 0)) {
                         // the tile's original fp64 rows ride behind the bf16 image in the same ring stage (written by the bulk
                         // copy: observe its barrier first; complete long ago, never blocks)
                         e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
                         const double *trows = reinterpret_cast<const double *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
-                        const int nreal = A.tile_rows[j];
-                        int cnt = 0;
-#pragma unroll
-                        for (int gq = 0; gq < 8; ++gq) {
-                            if (!__any_sync(0xffffffffu, (gmask >> gq) & 1u)) continue;
-#pragma unroll
-                            for (int c = gq * 8; c < gq * 8 + 8; ++c) {
-                                const bool pass = ((gmask >> gq) & 1u) && v[c] <= thr && c < nreal;
-                                if (pass) mylist[cnt] = (unsigned char)c;
-                                cnt += pass;
-                            }
-                        }
                         // every lane walks its own candidates; the loop length is the warp's longest list
                         const int row0 = A.tile_row0[j];
                         int longest = cnt;
@@ -444,15 +466,6 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                                         const double df = __dsub_rn(q[jj], t[jj]);
                                         dist = __dadd_rn(dist, __dmul_rn(df, df));
                                     }
-                                if (audit) {   // error statistic of the tensor-core value (every pair is listed in audit mode)
-                                    float accv = 0.f;
-#pragma unroll
-                                    for (int cc = 0; cc < 64; ++cc) accv = (cc == c) ? v[cc] : accv;
-                                    double tn = 0.0;
-                                    for (int jj = 0; jj < A.d; ++jj) { const double u = t[jj] - A.center[jj]; tn += u * u; }
-                                    const float ratio = (float)(fabs((double)accv - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
-                                    atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
-                                }
                                 ++n_exact;
                                 dep += (float)dist;
                                 if (dist < hv0) {
@@ -494,11 +507,11 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 float x32[kEMaxD];
 #pragma unroll
                 for (int j = 0; j < kEMaxD; ++j) x32[j] = (float)q[j];
-                float tsum[NC1];
+                float2 tsum[NC1];                                     // (even, odd) column partial sums: one FFMA2 per column pair
                 double csum[NC1];
                 double S[(NC1 + 1) * NC1];                            // S[i][m] = sum_{s in class i} coef[m][s] K_s (local memory)
 #pragma unroll
-                for (int m = 0; m < NC1; ++m) { tsum[m] = 0.f; csum[m] = 0.0; }
+                for (int m = 0; m < NC1; ++m) { tsum[m] = make_float2(0.f, 0.f); csum[m] = 0.0; }
                 for (int i = 0; i < (NC1 + 1) * NC1; ++i) S[i] = 0.0;
                 int cur_class = A.tile_class[0];
                 for (int j = 0; j < A.n_tiles; ++j, ++g) {
@@ -542,12 +555,11 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                             const float k1 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 1]), g2, bias));
                             const float k2 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 2]), g2, bias));
                             const float k3 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 3]), g2, bias));
+                            const float2 k01 = make_float2(k0, k1), k23 = make_float2(k2, k3);
 #pragma unroll
                             for (int m = 0; m < NC1; ++m) {
-                                tsum[m] = fmaf(cf[m].x, k0, tsum[m]);
-                                tsum[m] = fmaf(cf[m].y, k1, tsum[m]);
-                                tsum[m] = fmaf(cf[m].z, k2, tsum[m]);
-                                tsum[m] = fmaf(cf[m].w, k3, tsum[m]);
+                                e_fma2(tsum[m], make_float2(cf[m].x, cf[m].y), k01);
+                                e_fma2(tsum[m], make_float2(cf[m].z, cf[m].w), k23);
                             }
                         }
                     };
@@ -566,14 +578,14 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     {
                         float dep = xn;
 #pragma unroll
-                        for (int m = 0; m < NC1; ++m) dep += tsum[m];
+                        for (int m = 0; m < NC1; ++m) dep += tsum[m].x + tsum[m].y;
                         const uint32_t off = (dep == 1.2345e38f) ? 8u : 0u;   // never true for finite sums
                         __syncwarp();
                         if (lane == 0)
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
                     }
 #pragma unroll
-                    for (int m = 0; m < NC1; ++m) { csum[m] += (double)tsum[m]; tsum[m] = 0.f; }
+                    for (int m = 0; m < NC1; ++m) { csum[m] += (double)tsum[m].x + (double)tsum[m].y; tsum[m] = make_float2(0.f, 0.f); }
                 }
 #pragma unroll
                 for (int m = 0; m < NC1; ++m) S[cur_class * NC1 + m] = csum[m];
@@ -788,7 +800,15 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
         TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         kern<<<grid, kEThreads, smem, st>>>(A, x, labels, scores, E->d_counters);                                 \
     }
-    if (!svc) { if (heap_smem) TCSDN_LAUNCH(false, 1) else TCSDN_LAUNCH(false, 2) }
+    if (!svc) {
+        const int variant = (heap_smem ? 1 : 0) | (A.maxratio ? 2 : 0);
+        switch (variant) {
+            case 0: TCSDN_LAUNCH(false, 0) break;
+            case 1: TCSDN_LAUNCH(false, 1) break;
+            case 2: TCSDN_LAUNCH(false, 2) break;
+            default: TCSDN_LAUNCH(false, 3) break;
+        }
+    }
     else switch (E->nc1) {
         case 1: TCSDN_LAUNCH(true, 1) break;
         case 2: TCSDN_LAUNCH(true, 2) break;
