@@ -6,7 +6,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 NCU=${NCU:-ncu}
 # every launch of the default bench with its device time (cold-cache, serialised: compare shares, not absolutes)
-timeout 1200 $NCU --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+timeout 1200 $NCU --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 5 --warmup 3 > gpurun_out/launches_${TAG}.stdout 2> gpurun_out/launches_${TAG}.stderr
 prof() {  # name kernel-regex command...
     local NAME=$1 RE=$2; shift 2
@@ -19,3 +19,7 @@ prof forest forest_kernel python bench.py --workload forest --no-extras --steps 
 prof forest_hbm forest_kernel python bench.py --workload forest_hbm --no-extras --steps 3 --warmup 3
 prof svc engine_kernel python tools/run_workload.py svc 10000000 4
 prof knn engine_kernel python tools/run_workload.py knn 10000000 4
+# summarise on the box (only gpurun_out/ travels back, 64 MiB at most) and drop the bulky reports that are not needed again
+python tools/make_profile_summary.py ${TAG} gpurun_out/profiles > gpurun_out/summary_${TAG}.log 2>&1
+rm -f gpurun_out/prof_${TAG}_logistic.ncu-rep gpurun_out/prof_${TAG}_forest_hbm.ncu-rep gpurun_out/prof_${TAG}_gnb.ncu-rep
+du -sh gpurun_out

@@ -4,7 +4,8 @@ usage: tools/make_profile_summary.py <tag>"""
 import csv, json, os, subprocess, sys, collections
 tag = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, sys.argv[2] if len(sys.argv) > 2 else "profiles")
+os.makedirs(P, exist_ok=True)
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
