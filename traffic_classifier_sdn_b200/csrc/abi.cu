@@ -397,6 +397,14 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
     }
     if (chunk > n) chunk = n;
     const size_t sc_cols = scores_out ? (size_t)m->score_cols : 0;
+    // results go straight into the caller's arrays when those are page-locked (cudaHostAlloc / cudaHostRegister);
+    // pageable arrays are filled from pinned staging buffers
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct_out = is_pinned(labels_out) && (!sc_cols || is_pinned(scores_out));
     Workspace *w = nullptr;
     TCSDN_TRY(acquire_workspace(m, &w));
     int rc = TCSDN_OK;
@@ -405,10 +413,12 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
         if (pend_off[slot] < 0) return TCSDN_OK;
         cudaError_t e = cudaEventSynchronize(w->done[slot]);
         if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
-        memcpy(labels_out + pend_off[slot], w->h_labels[slot], (size_t)pend_rows[slot] * sizeof(int32_t));
-        if (sc_cols)
-            memcpy(scores_out + (size_t)pend_off[slot] * sc_cols, w->h_scores[slot],
-                   (size_t)pend_rows[slot] * sc_cols * sizeof(double));
+        if (!direct_out) {
+            memcpy(labels_out + pend_off[slot], w->h_labels[slot], (size_t)pend_rows[slot] * sizeof(int32_t));
+            if (sc_cols)
+                memcpy(scores_out + (size_t)pend_off[slot] * sc_cols, w->h_scores[slot],
+                       (size_t)pend_rows[slot] * sc_cols * sizeof(double));
+        }
         pend_off[slot] = -1;
         return TCSDN_OK;
     };
@@ -427,10 +437,10 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
             if ((rc = drain(slot)) != TCSDN_OK) break;
             if ((rc = ensure(w->x[slot], (size_t)chunk * row_bytes)) != TCSDN_OK) break;
             if ((rc = ensure(w->labels[slot], (size_t)chunk * sizeof(int32_t))) != TCSDN_OK) break;
-            if ((rc = ensure_pinned(&w->h_labels[slot], &w->h_labels_bytes[slot], (size_t)chunk * sizeof(int32_t))) != TCSDN_OK) break;
+            if (!direct_out && (rc = ensure_pinned(&w->h_labels[slot], &w->h_labels_bytes[slot], (size_t)chunk * sizeof(int32_t))) != TCSDN_OK) break;
             if (sc_cols) {
                 if ((rc = ensure(w->scores[slot], (size_t)chunk * sc_cols * sizeof(double))) != TCSDN_OK) break;
-                if ((rc = ensure_pinned(&w->h_scores[slot], &w->h_scores_bytes[slot], (size_t)chunk * sc_cols * sizeof(double))) != TCSDN_OK) break;
+                if (!direct_out && (rc = ensure_pinned(&w->h_scores[slot], &w->h_scores_bytes[slot], (size_t)chunk * sc_cols * sizeof(double))) != TCSDN_OK) break;
             }
             cudaError_t e = cudaMemcpyAsync(w->x[slot].p, static_cast<const char *>(x) + (size_t)done * row_bytes,
                                             (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st);
@@ -438,10 +448,11 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
             rc = run_device(m, w->x[slot].p, rows, x_dtype, static_cast<int32_t *>(w->labels[slot].p),
                             sc_cols ? static_cast<double *>(w->scores[slot].p) : nullptr, st);
             if (rc != TCSDN_OK) break;
-            e = cudaMemcpyAsync(w->h_labels[slot], w->labels[slot].p, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(direct_out ? (void *)(labels_out + done) : w->h_labels[slot], w->labels[slot].p,
+                                (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess && sc_cols)
-                e = cudaMemcpyAsync(w->h_scores[slot], w->scores[slot].p, (size_t)rows * sc_cols * sizeof(double),
-                                    cudaMemcpyDeviceToHost, st);
+                e = cudaMemcpyAsync(direct_out ? (void *)(scores_out + (size_t)done * sc_cols) : w->h_scores[slot],
+                                    w->scores[slot].p, (size_t)rows * sc_cols * sizeof(double), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaEventRecord(w->done[slot], st);
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; break; }
             pend_off[slot] = done; pend_rows[slot] = rows;
