@@ -36,8 +36,8 @@ INT_LABELS = {0: "dns", 1: "game", 2: "ping", 3: "quake", 4: "telnet", 5: "voice
 FIELDS = ["Flow ID", "Src MAC", "Dest MAC", "Traffic Type", "Forward Status", "Reverse Status"]
 
 
-def print_help(out=sys.stdout):
-    w = out.write
+def print_help(out=None):
+    w = (out or sys.stdout).write
     w("\nUsage: sudo python traffic_classifier.py [subcommand] [options]\n")
     w("\n\tTo collect training data for a certain type of traffic, run: sudo python traffic_classifier.py train <TypeOfData>\n")
     w("\n\tTo start a near real time traffic classification application using unsupervised ML, run: sudo python traffic_classifier.py <NameOfAlgo>\n")
@@ -46,8 +46,9 @@ def print_help(out=sys.stdout):
     w("\n\t SUBCOMMANDS = ('train', 'logistic', 'kmeans', 'knearest', 'svm', 'Randomforest', 'gaussiannb')\n")
 
 
-def render_table(rows, out=sys.stdout):
+def render_table(rows, out=None):
     """ASCII table in PrettyTable's default style (prettytable is not a dependency here)."""
+    out = out or sys.stdout
     cells = [FIELDS] + [[str(c) for c in r] for r in rows]
     widths = [max(len(r[i]) for r in cells) for i in range(len(FIELDS))]
     sep = "+" + "+".join("-" * (w + 2) for w in widths) + "+"
@@ -75,7 +76,7 @@ def classify_table(table: _flows.FlowTable, model):
     return rows
 
 
-def run_monitor(stream, model=None, traffic_type=None, f=None, every=10, out=sys.stdout, max_lines=None):
+def run_monitor(stream, model=None, traffic_type=None, f=None, every=10, out=None, max_lines=None):
     """reference run_ryu (:144-171) over any binary line stream.  Unlike the reference, which never leaves its
     loop (``out == ''`` compares bytes to str, :150), this returns at end of stream."""
     table = _flows.FlowTable()
