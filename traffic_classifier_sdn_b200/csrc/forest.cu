@@ -14,25 +14,24 @@
 // impure leaf indexes a table of fp64 fraction vectors kept in HBM (see walk_group for the bit layout).  Trees are packed, in estimator order, into groups that fit the shared
 // memory tree buffer.
 //
-// Kernel.  A CTA owns a tile of 1024 rows: the tile is staged transposed in shared memory
+// Kernel.  A CTA (1024 threads, one row each) owns a tile of 1024 rows: the tile is staged transposed in shared memory
 // (xs[f][row]: every lane reads its own bank whatever feature its node tests), per-row fp64
 // class accumulators live in shared memory next to it, and each group of trees is streamed from L2
-// into the tree buffer once per tile.  A thread walks its two rows through the group's trees one
+// into the tree buffer once per tile.  A thread walks its row through the group's trees one
 // tree after another without re-converging with its neighbours (a lane that reaches a leaf starts
 // the next tree at once), adding each tree's fractions to its accumulators in tree order -- the
 // same fp64 addition sequence as sklearn's `out += proba`, hence identical bits.
 // Trees larger than the buffer are walked in place in HBM/L2.
 // Algorithmic bytes per row: 4*d in + 4 out (+ 8 per node visit).
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
 
 namespace tcsdn {
 
-constexpr int kFThreads = 512;
-constexpr int kRPT = 2;                       // rows per thread
-constexpr int kFRows = kFThreads * kRPT;      // rows per tile
+constexpr int kFRows = 1024;                  // rows per tile (= threads x rows per thread)
 constexpr uint32_t kLeaf = 0x80000000u;
 constexpr uint32_t kNegInf = 0xFF800000u;   // x of a pure leaf and of the halt node; impure leaves use 0xFFC00000 | index
 
@@ -74,7 +73,7 @@ __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
         : "memory");
 }
 
-template <bool IN_SMEM>
+template <bool IN_SMEM, int kFThreads, int kRPT>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_t halt, const float *xs, double *acc,
                                            const double *leaf_val, int C, int r0, int nrows_live) {
     uint32_t pos[kRPT];
@@ -112,7 +111,7 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_
     }
 }
 
-template <typename T>
+template <typename T, int kFThreads, int kRPT>
 __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_constant__ ForestArgs A,
                                                               const T *__restrict__ X,
                                                               int32_t *__restrict__ labels,
@@ -166,9 +165,9 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             }
             __syncthreads();
             if (in_smem)
-                walk_group<true>(snodes, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
+                walk_group<true, kFThreads, kRPT>(snodes, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
             else
-                walk_group<false>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
+                walk_group<false, kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
         }
         // each thread finalises its own rows (only it touched their accumulators)
 #pragma unroll
@@ -325,9 +324,10 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
     return TCSDN_OK;
 }
 
-template <typename T>
-static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
-    auto kern = forest_kernel<T>;
+template <typename T, int kFThreads, int kRPT>
+static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+    static_assert(kFThreads * kRPT == kFRows, "tile geometry");
+    auto kern = forest_kernel<T, kFThreads, kRPT>;
     const int64_t fixed = (int64_t)(m->d > m->n_classes ? m->d : m->n_classes) * kFRows * 4 + (int64_t)m->n_classes * kFRows * 8;
     int64_t buf_nodes = (m->max_group_nodes > 0 ? m->max_group_nodes : 0) + 1;   // largest in-smem group + its halt node
     if (buf_nodes < 64) buf_nodes = 64;
@@ -342,6 +342,18 @@ static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, m->opt_check_finite ? m->d_flag : nullptr);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
+}
+
+template <typename T>
+static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+    // threads x rows-per-thread.  Measured on the 100-tree sklearn forest (12.5M rows): 256 x 4 -> 3.8e8 rows/s,
+    // 512 x 2 -> 6.3e8, 1024 x 1 -> 8.2e8: the walk is a chain of dependent shared-memory loads, and 32 warps hide its
+    // latency better than instruction-level parallelism inside 8 or 16.  TCSDN_FOREST_CFG (0, 1) selects the others.
+    static int cfg = -1;
+    if (cfg < 0) { const char *e = getenv("TCSDN_FOREST_CFG"); cfg = e ? atoi(e) : 2; }
+    if (cfg == 0) return launch_forest_cfg<T, 512, 2>(m, x, n, labels, scores, st);
+    if (cfg == 1) return launch_forest_cfg<T, 256, 4>(m, x, n, labels, scores, st);
+    return launch_forest_cfg<T, 1024, 1>(m, x, n, labels, scores, st);
 }
 
 int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
