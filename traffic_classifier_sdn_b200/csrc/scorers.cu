@@ -22,15 +22,13 @@
 // Error: |delta t| <= u |theta s| + u |t|, i.e. the joint log likelihood is exact to ~1e-16 * (theta/sigma)
 // relative to its own terms (<= 1e-11 of the row's largest |jll| in the tests, labels unchanged).
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.h"
 
 namespace tcsdn {
 
-constexpr int kThreads = 128;  // threads per CTA
-constexpr int kRPT = 4;        // rows per thread: the model's constants are fetched once per 4 rows
-constexpr int kTile = kThreads * kRPT;   // rows per tile
-constexpr int kStages = 3;
+constexpr int kStages = 3;     // shared-memory ring depth; tile = kThreads x kRPT rows (template parameters below)
 
 enum : int { KIND_AFFINE_MAX = 0, KIND_AFFINE_MIN = 1, KIND_GNB = 2 };
 
@@ -87,7 +85,7 @@ __device__ __forceinline__ void load_row_smem(const T *tile, int r, double (&x)[
 
 // Scores kRPT rows at once: for every (class r, feature j) the constants are read once and applied to all rows,
 // which keeps the constant-bank traffic (one LDC per operand) off the fp64 pipe's critical path.
-template <int D, int R, int KIND>
+template <int D, int R, int KIND, int kRPT>
 __device__ __forceinline__ void score_rows(const ScorerParams &P, const double (&x)[kRPT][D], double (&s)[kRPT][R],
                                            int (&arg)[kRPT]) {
 #pragma unroll
@@ -127,12 +125,13 @@ __device__ __forceinline__ void score_rows(const ScorerParams &P, const double (
     }
 }
 
-template <typename T, int D, int R, int KIND>
+template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
 __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
                                                                 const T *__restrict__ X, int64_t n,
                                                                 int32_t *__restrict__ labels,
                                                                 double *__restrict__ scores, int32_t *flag) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kTile = kThreads * kRPT;
     constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
     T *tiles = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTileBytes);
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
         }
         double s[kRPT][R];
         int arg[kRPT];
-        score_rows<D, R, KIND>(P, x, s, arg);
+        score_rows<D, R, KIND, kRPT>(P, x, s, arg);
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {
             const int64_t row = row0 + q * kThreads + tid;
@@ -245,10 +244,11 @@ __global__ void __launch_bounds__(256) scorer_generic_kernel(const T *__restrict
     if (flag && nf != nf) atomicOr(flag, 1);
 }
 
-template <typename T, int D, int R, int KIND>
-static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
-                        cudaStream_t st) {
-    auto kern = scorer_tiled_kernel<T, D, R, KIND>;
+template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
+static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                            cudaStream_t st, int ctas_per_sm) {
+    constexpr int kTile = kThreads * kRPT;
+    auto kern = scorer_tiled_kernel<T, D, R, KIND, kThreads, kRPT>;
     const size_t smem = (size_t)kStages * kTile * D * sizeof(T) + kStages * sizeof(uint64_t);
     static bool configured = false;  // per instantiation
     if (!configured) {
@@ -256,7 +256,6 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
         configured = true;
     }
     int64_t n_tiles = (n + kTile - 1) / kTile;
-    int ctas_per_sm = sizeof(T) == 4 ? 3 : 2;
     int64_t grid = (int64_t)m->sm_count * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     // (Programmatic dependent launch was tried here -- griddepcontrol.wait/launch_dependents with the PDL launch
@@ -265,6 +264,21 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
     kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
+}
+
+template <typename T, int D, int R, int KIND>
+static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                        cudaStream_t st) {
+    // CTA shape (measured on B200, 1M x 8 GaussianNB / 10M x 12 LogisticRegression, rows/s):
+    //   128 threads x 4 rows: 8.3e10 / 1.105e11    256 x 2: 7.9e10 / 1.132e11    256 x 4: 7.7e10 / 9.7e10    128 x 8: 8.3e10 / 7.7e10
+    // GaussianNB (fp64-pipe-bound) wants the constants amortised over 4 rows, the HBM-bound max/min scorers want more warps.
+    // TCSDN_SCORER_CFG=0/1 forces 128 x 4 / 256 x 2.
+    static int cfg = -1;
+    if (cfg < 0) { const char *e = getenv("TCSDN_SCORER_CFG"); cfg = e ? atoi(e) : 2; }
+    const int per_sm = sizeof(T) == 4 ? 3 : 2;
+    const bool wide = cfg == 2 ? KIND != KIND_GNB : cfg == 1;
+    if (wide) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm);
+    return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm);
 }
 
 template <typename T, int D, int KIND>
