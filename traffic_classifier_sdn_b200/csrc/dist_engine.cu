@@ -52,6 +52,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.h"
@@ -72,7 +74,9 @@ constexpr int kEMaxK = 32;                  // neighbours kept per query in the 
 constexpr int kEMaxNC1 = 7;                 // SVC: n_classes - 1
 constexpr float kKappa = 1.0f / 262144.0f;  // 2^-18: filter slack per unit of (||x||^2 + ||t||^2); 8x the largest error the
                                             // all-pairs audit observes (2^-21.0 .. 2^-20.4, tests/test_engine_gpu.py)
-constexpr int kEListCap = 64;               // per-thread candidate list (one slot per column of a tile)
+constexpr int kEListCap = 24;               // per-thread candidate list, 16-bit entries (tile offset, group of 8 columns, mask)
+constexpr int kEListRoom = 8;               // one tile appends at most this many: lists are evaluated beyond cap - room
+constexpr int kEFlushTiles = 31;            // default number of reference tiles between two evaluation rounds (KNN), <= 31
 
 struct EngineState {
     unsigned char *d_tiles = nullptr;   // tile images
@@ -80,6 +84,7 @@ struct EngineState {
     int32_t *d_tile_row0 = nullptr;     // per tile: index of its first reference row in the ORIGINAL order
     int32_t *d_tile_rows = nullptr;     // per tile: number of real rows
     double *d_center = nullptr;         // [d]
+    double *d_refpad = nullptr;         // KNN: original fp64 reference rows, row stride padded to an even count (16 B loads)
     float *d_maxratio = nullptr;        // audit: max observed |acc - exact| / (||x||^2 + ||t||^2)
     unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN)
     int n_tiles = 0;
@@ -93,13 +98,14 @@ struct EngineArgs {
     const int32_t *tile_row0;
     const int32_t *tile_rows;
     const double *center;
-    const double *ref;       // original fp64 reference rows (KNN exact re-evaluation)
+    const double *ref;       // original fp64 reference rows (audit statistic)
+    const double *refpad;    // the same rows at a 16-byte-aligned stride of dpad doubles (KNN exact re-evaluation)
     const int32_t *y;        // KNN labels
     const double *rho;       // SVC
     float *maxratio;         // non-null = audit mode
     int32_t *flag;
     int64_t n;
-    int n_tiles, tile_bytes, d, k, C, nc1;
+    int n_tiles, tile_bytes, d, dpad, k, C, nc1, flush_tiles, n_ref;
     float g2;                // SVC: -gamma * log2(e)
 };
 
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 for (int j = 0; j < A.n_tiles; ++j, ++g) {
                     const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
                     e_mbar_wait(&emptyB[s], ph ^ 1);
-                    e_mbar_wait(&coefFree[s], ph ^ 1);   // the epilogue warps are done with the stage's side data
+                    if (SVC) e_mbar_wait(&coefFree[s], ph ^ 1);   // the epilogue warps are done with the stage's coefficients
                     e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
                     e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)j * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
                 }
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
             const int64_t row = st * kERows + qt * 128 + rt;
             const bool live = row < A.n;
             // ---- load, centre, split and pack this row into the A operand
-            double q[kEMaxD];
+            T qx[kEMaxD];
             double qn = 0.0;
             {
                 __align__(16) __nv_bfloat16 pk[kEK];
@@ -346,12 +352,12 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 for (int i = 0; i < kEK; ++i) pk[i] = __float2bfloat16_rn(0.f);
 #pragma unroll
                 for (int j = 0; j < kEMaxD; ++j) {
-                    q[j] = 0.0;
+                    qx[j] = static_cast<T>(0);
                     if (j < A.d && live) {
                         const T v = X[row * A.d + j];
                         nf += static_cast<float>(v * static_cast<T>(0));
-                        q[j] = static_cast<double>(v);
-                        const float c32 = static_cast<float>(q[j] - A.center[j]);
+                        qx[j] = v;
+                        const float c32 = static_cast<float>(static_cast<double>(v) - A.center[j]);
                         qn += (double)c32 * (double)c32;
                         __nv_bfloat16 h, m, l;
                         split3(-2.0f * c32, h, m, l);
@@ -372,119 +378,143 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
             if (lane == 0) e_mbar_arrive(aFull);
 
             if constexpr (!SVC) {
-                // ================================================================ KNN: filter + exact heap
+                // ================================================================ KNN: filter, deferred exact heap
                 // acc = (1 - kappa) ||t||^2 - 2 x.t, so a row passes iff acc <= thr = (worst kept distance - ||x||^2)
-                // + kappa ||x||^2.  Passing columns are listed per thread, then every lane walks its own list: exact
-                // fp64 distance (sklearn's rdist order) + heap_push, in column = training-index order.
-                // The k-slot max-heap: shared memory [slot][thread] for k <= 8 (template NC1 == 1), else thread-private local
-                // memory (NC1 == 2).  Its root and the filter threshold stay in registers: the common "candidate is not
-                // better than the worst kept one" test touches no memory.
+                // + kappa ||x||^2.  Passing columns are appended to a per-thread list (tile offset << 6 | column) and the
+                // lists are evaluated every `flush_tiles` tiles (or when one runs full): exact fp64 distance in sklearn's
+                // rdist order from the original rows (L2-resident), then heap_push -- per query still in training-index
+                // order, so the heap is the sequential one.  Deferral only makes the threshold staler, i.e. the filter a
+                // little more permissive; what it buys is warp efficiency: evaluating right after every tile kept ~5 of 32
+                // lanes busy (most lanes have no candidate in a given tile), batching 16 tiles keeps about half of them busy,
+                // and all 16 warps evaluate at the same tile indices instead of stalling each other through the two
+                // accumulator buffers.
+                // The k-slot max-heap: shared memory [slot][thread] for k <= 8 (NC1 bit 0), else thread-private local
+                // memory.  Its root and the filter threshold stay in registers.
                 constexpr bool kHeapSmem = (NC1 & 1) != 0;      // KNN instantiations: NC1 bit 0 = heap in shared memory,
                 constexpr bool kAudit = (NC1 & 2) != 0;         //                     bit 1 = audit mode (error statistic)
                 constexpr int ST = kHeapSmem ? 512 : 1;
                 double hv_local[kHeapSmem ? 1 : kEMaxK];
                 int32_t hi_local[kHeapSmem ? 1 : kEMaxK];
-                double *hv = kHeapSmem ? reinterpret_cast<double *>(cand + 512 * kEListCap) + tid : hv_local;
-                int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(cand + 512 * kEListCap + 512 * kEHeapSmemK * 8) + tid : hi_local;
+                unsigned char *heap_base = cand + 512 * kEListCap * sizeof(uint16_t);
+                double *hv = kHeapSmem ? reinterpret_cast<double *>(heap_base) + tid : hv_local;
+                int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(heap_base + 512 * (size_t)A.k * sizeof(double)) + tid : hi_local;
                 for (int i = 0; i < A.k; ++i) { hv[i * ST] = DBL_MAX; hi[i * ST] = 0; }
                 double hv0 = DBL_MAX;
                 float thr_base = FLT_MAX;
                 unsigned long long n_exact = 0;
-                unsigned char *mylist = cand + (size_t)tid * kEListCap;
-                constexpr bool audit = kAudit;
-                float dep = 0.f;   // consumes every shared-memory load of the candidate loop (see the stage release below)
-                for (int j = 0; j < A.n_tiles; ++j, ++g) {
-                    const uint32_t sidx = g % kEStages;
+                // candidate list entries: tile offset since the last round << 11 | group of 8 columns << 8 | pass mask
+                uint16_t *mylist = reinterpret_cast<uint16_t *>(cand) + (size_t)tid * kEListCap;
+                int cnt = 0, base_tile = 0;
+                const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(qt * 2 * kEN);
+#pragma unroll 1
+                for (int j = 0; j <= A.n_tiles; ++j) {
+                    // ---- evaluation round: at the end, every `period` tiles (short while the threshold is still falling
+                    // fast), or when a list could overflow in this tile
+                    const int period = min(A.flush_tiles, 1 + (j >> 2));
+                    const bool due = j == A.n_tiles || j - base_tile >= period;
+                    if (due || __any_sync(0xffffffffu, cnt > kEListCap - kEListRoom)) {
+                        int li = 0, gbase = 0;
+                        uint32_t m = 0;
+                        auto next = [&](int32_t &idx) -> bool {   // pops this thread's next candidate (training index order)
+                            if (m == 0) {
+                                if (li >= cnt) return false;
+                                const uint32_t e = mylist[li++];
+                                m = e & 255u;
+                                gbase = ((base_tile + (int)(e >> 11)) << 6) + (int)((e >> 8) & 7u) * 8;
+                            }
+                            idx = gbase + __ffs(m) - 1;
+                            m &= m - 1;
+                            return true;
+                        };
+                        // two candidates per round: two independent fp64 chains and twelve 16-byte loads in flight
+                        for (;;) {
+                            int32_t ia = 0, ib = 0;   // (an idle slot reads row 0 and discards the result)
+                            const bool pa = next(ia);
+                            const bool pb = pa && next(ib);
+                            if (!__any_sync(0xffffffffu, pa)) break;
+                            const double2 *ta = reinterpret_cast<const double2 *>(A.refpad + (size_t)ia * A.dpad);
+                            const double2 *tb = reinterpret_cast<const double2 *>(A.refpad + (size_t)ib * A.dpad);
+                            double da = 0.0, db = 0.0;
+#pragma unroll
+                            for (int jj = 0; jj < kEMaxD; jj += 2)
+                                if (jj < A.d) {
+                                    const double2 va = __ldg(ta + (jj >> 1)), vb = __ldg(tb + (jj >> 1));
+                                    const double q0 = static_cast<double>(qx[jj]);
+                                    double df = __dsub_rn(q0, va.x);
+                                    da = __dadd_rn(da, __dmul_rn(df, df));
+                                    df = __dsub_rn(q0, vb.x);
+                                    db = __dadd_rn(db, __dmul_rn(df, df));
+                                    if (jj + 1 < A.d) {
+                                        const double q1 = static_cast<double>(qx[jj + 1]);
+                                        df = __dsub_rn(q1, va.y);
+                                        da = __dadd_rn(da, __dmul_rn(df, df));
+                                        df = __dsub_rn(q1, vb.y);
+                                        db = __dadd_rn(db, __dmul_rn(df, df));
+                                    }
+                                }
+                            n_exact += (unsigned)pa + (unsigned)pb;
+                            if (pa && da < hv0) { knn_heap_push<ST>(hv, hi, A.k, da, ia); hv0 = hv[0]; }
+                            if (pb && db < hv0) { knn_heap_push<ST>(hv, hi, A.k, db, ib); hv0 = hv[0]; }
+                        }
+                        thr_base = knn_thr_base(hv0, qn);
+                        cnt = 0;
+                        base_tile = j;
+                    }
+                    if (j == A.n_tiles) break;
+                    // ---- filter one reference tile: two halves of 32 accumulator columns (keeps 32, not 64, values live)
                     const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                    ++g;
                     e_mbar_wait(&accFull[b], bph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const float thr = !live ? -FLT_MAX : (audit ? FLT_MAX : thr_base);
-                    const int nreal = A.tile_rows[j];
-                    int cnt = 0;
-                    // two halves of 32 columns (keeps 32, not 64, accumulator values live): group minima first -- the common
-                    // case is "nothing in this group of 8 passes" -- then the passing columns are listed
+                    const float thr = !live ? -FLT_MAX : (kAudit ? FLT_MAX : thr_base);
+                    const uint32_t etile = (uint32_t)(j - base_tile) << 11;
+                    uint32_t lp = e_smem(mylist) + 2u * (uint32_t)cnt;   // 32-bit shared address of the list's tail
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         float v[32];
-                        e_tmem_ld32(tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN + h * 32), v);
+                        e_tmem_ld32(taddr0 + b * kEN + h * 32, v);
                         if (h == 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
                         }
-                        uint32_t gmask = 0;
+                        // group minima first: two halves out of three hold nothing for any lane of the warp.  Padding
+                        // columns carry +inf and never pass.
+                        float gm[4];
 #pragma unroll
                         for (int gq = 0; gq < 4; ++gq) {
                             const float m0 = e_min3(v[gq * 8 + 0], v[gq * 8 + 1], v[gq * 8 + 2]);
                             const float m1 = e_min3(v[gq * 8 + 3], v[gq * 8 + 4], v[gq * 8 + 5]);
-                            if (e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7])) <= thr) gmask |= 1u << gq;
+                            gm[gq] = e_min3(m0, m1, fminf(v[gq * 8 + 6], v[gq * 8 + 7]));
                         }
-                        if (__any_sync(0xffffffffu, gmask != 0)) {
+                        if (!__any_sync(0xffffffffu, e_min3(gm[0], gm[1], fminf(gm[2], gm[3])) <= thr)) continue;
 #pragma unroll
-                            for (int gq = 0; gq < 4; ++gq) {
-                                if (!__any_sync(0xffffffffu, (gmask >> gq) & 1u)) continue;
+                        for (int gq = 0; gq < 4; ++gq) {
+                            if (!__any_sync(0xffffffffu, gm[gq] <= thr)) continue;
+                            uint32_t mask = 0;
 #pragma unroll
-                                for (int c = gq * 8; c < gq * 8 + 8; ++c) {
-                                    const bool pass = ((gmask >> gq) & 1u) && v[c] <= thr && (h * 32 + c) < nreal;
-                                    if (pass) mylist[cnt] = (unsigned char)(h * 32 + c);
-                                    cnt += pass;
-                                    if constexpr (kAudit) {   // error statistic while the accumulator value is at hand
-                                        if (pass) {
-                                            const double *t = A.ref + (size_t)(A.tile_row0[j] + h * 32 + c) * A.d;
-                                            double dist = 0.0, tn = 0.0;
-                                            for (int jj = 0; jj < A.d; ++jj) {
-                                                const double df = q[jj] - t[jj], u = t[jj] - A.center[jj];
-                                                dist += df * df; tn += u * u;
-                                            }
-                                            const float ratio = (float)(fabs((double)v[c] - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
-                                            atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
+                            for (int c = 0; c < 8; ++c) mask |= (v[gq * 8 + c] <= thr) ? (1u << c) : 0u;
+                            if (mask) asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp), "h"((uint16_t)(etile | (uint32_t)((h * 4 + gq) << 8) | mask)) : "memory");
+                            lp += mask ? 2u : 0u;
+                            if constexpr (kAudit) {   // error statistic while the accumulator values are at hand
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const int tr = j * kEN + h * 32 + gq * 8 + c;
+                                    if (((mask >> c) & 1u) && tr < A.n_ref) {
+                                        const double *t = A.ref + (size_t)tr * A.d;
+                                        double dist = 0.0, tn = 0.0;
+                                        for (int jj = 0; jj < A.d; ++jj) {
+                                            const double df = static_cast<double>(qx[jj]) - t[jj], u = t[jj] - A.center[jj];
+                                            dist += df * df; tn += u * u;
                                         }
+                                        const float ratio = (float)(fabs((double)v[gq * 8 + c] - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
+                                        atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int(ratio));
                                     }
                                 }
                             }
                         }
                     }
-                    if (__any_sync(0xffffffffu, cnt != 0)) {
-                        // the tile's original fp64 rows ride behind the bf16 image in the same ring stage (written by the bulk
-                        // copy: observe its barrier first; complete long ago, never blocks)
-                        e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
-                        const double *trows = reinterpret_cast<const double *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
-                        // every lane walks its own candidates; the loop length is the warp's longest list
-                        const int row0 = A.tile_row0[j];
-                        int longest = cnt;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
-                        for (int i = 0; i < longest; ++i) {
-                            if (i < cnt) {
-                                const int c = mylist[i];
-                                const int32_t idx = row0 + c;
-                                const double *t = trows + c * A.d;
-                                double dist = 0.0;
-#pragma unroll
-                                for (int jj = 0; jj < kEMaxD; ++jj)
-                                    if (jj < A.d) {
-                                        const double df = __dsub_rn(q[jj], t[jj]);
-                                        dist = __dadd_rn(dist, __dmul_rn(df, df));
-                                    }
-                                ++n_exact;
-                                dep += (float)dist;
-                                if (dist < hv0) {
-                                    knn_heap_push<ST>(hv, hi, A.k, dist, idx);
-                                    hv0 = hv[0];
-                                    thr_base = knn_thr_base(hv0, qn);
-                                }
-                            }
-                        }
-                    }
-                    // release the stage: the barrier address depends on every value loaded from it (mbarrier.arrive does not
-                    // wait for outstanding ld.shared, see the file header)
-                    {
-                        // the candidate loads run under divergence, so lane 0 must depend on EVERY lane's loads: a warp vote
-                        const uint32_t off = __any_sync(0xffffffffu, dep == -1.0f) ? 8u : 0u;   // never true: dep sums squared distances
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
-                    }
+                    cnt = (int)((lp - e_smem(mylist)) >> 1);
                 }
                 if (live) {
                     int best = 0, arg = 0;
@@ -506,7 +536,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 const float g2 = A.g2;
                 float x32[kEMaxD];
 #pragma unroll
-                for (int j = 0; j < kEMaxD; ++j) x32[j] = (float)q[j];
+                for (int j = 0; j < kEMaxD; ++j) x32[j] = (float)qx[j];
                 float2 tsum[NC1];                                     // (even, odd) column partial sums: one FFMA2 per column pair
                 double csum[NC1];
                 double S[(NC1 + 1) * NC1];                            // S[i][m] = sum_{s in class i} coef[m][s] K_s (local memory)
@@ -663,8 +693,10 @@ static void compact_order(const std::vector<double> &ref, int d, std::vector<int
     compact_order(ref, d, idx, mid, hi);
 }
 
-static void pack_dummy(unsigned char *tile, int r, int d) {  // a row that is "infinitely" far from everything
-    const __nv_bfloat16 big = __float2bfloat16_rn(1e30f);
+// a padding row that is "infinitely" far from everything.  KNN: +inf, so that it fails the filter even while the
+// threshold is still FLT_MAX (A's norm slot is 1.0 and the row's other entries are 0: no 0 x inf).  SVC: 1e30, ex2 -> 0.
+static void pack_dummy(unsigned char *tile, int r, int d, bool inf) {
+    const __nv_bfloat16 big = __float2bfloat16_rn(inf ? INFINITY : 1e30f);
     memcpy(tile + tile_off(r, 6 * d + 0), &big, 2);
 }
 
@@ -691,9 +723,8 @@ int engine_create(tcsdn_model *m) {
     EngineState *E = new EngineState();
     const int nc1 = svc ? m->n_classes - 1 : 0;
     E->nc1 = nc1;
-    // tile image = bf16 B operand, then SVC: dual coefficients + tile centre; KNN: the tile's original fp64 rows
-    E->tile_bytes = kETileB + (svc ? nc1 * kEN * (int)sizeof(float) + 16 * (int)sizeof(float)
-                                   : ((kEN * d * (int)sizeof(double) + 15) / 16) * 16);
+    // tile image = bf16 B operand, then (SVC only) the tile's dual coefficients + centre
+    E->tile_bytes = kETileB + (svc ? nc1 * kEN * (int)sizeof(float) + 16 * (int)sizeof(float) : 0);
     // tile plan: KNN = consecutive rows in the original order (the heap semantics need index order);
     // SVC = per class (sums are per class), rows re-ordered inside the class for spatial compactness (sums do not
     // care about order), padded to a tile boundary with zero-coefficient rows
@@ -739,15 +770,19 @@ int engine_create(tcsdn_model *m) {
                 if (svc) {
                     float *cf = reinterpret_cast<float *>(tile + kETileB);
                     for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + src]);
-                } else {
-                    memcpy(tile + kETileB + (size_t)r * d * sizeof(double), &ref[(size_t)src * d], (size_t)d * sizeof(double));
                 }
             } else {
-                pack_dummy(tile, r, d);
+                pack_dummy(tile, r, d, !svc);
             }
         }
     }
     int rc = upload(&E->d_tiles, img.data(), img.size());
+    if (rc == TCSDN_OK && !svc) {   // exact re-evaluation reads the original rows with 16-byte loads: even row stride
+        const int dpad = (d + 1) & ~1;
+        std::vector<double> pad((size_t)nref * dpad, 0.0);
+        for (int64_t i = 0; i < nref; ++i) memcpy(&pad[(size_t)i * dpad], &ref[(size_t)i * d], (size_t)d * sizeof(double));
+        rc = upload(&E->d_refpad, pad.data(), pad.size());
+    }
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_class, tclass.data(), tclass.size());
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_row0, row0.data(), row0.size());
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_rows, rows.data(), rows.size());
@@ -765,7 +800,7 @@ void engine_destroy(tcsdn_model *m) {
     EngineState *E = static_cast<EngineState *>(m->engine);
     if (!E) return;
     cudaFree(E->d_tiles); cudaFree(E->d_tile_class); cudaFree(E->d_tile_row0); cudaFree(E->d_tile_rows);
-    cudaFree(E->d_center); cudaFree(E->d_maxratio); cudaFree(E->d_counters);
+    cudaFree(E->d_center); cudaFree(E->d_refpad); cudaFree(E->d_maxratio); cudaFree(E->d_counters);
     delete E;
     m->engine = nullptr;
 }
@@ -788,10 +823,15 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     A.maxratio = m->opt_engine == 3 ? E->d_maxratio : nullptr;
     A.flag = m->opt_check_finite ? m->d_flag : nullptr; A.n = n; A.n_tiles = E->n_tiles;
     A.tile_bytes = E->tile_bytes; A.d = m->d; A.k = m->k; A.C = m->n_classes; A.nc1 = E->nc1;
+    A.refpad = E->d_refpad; A.dpad = (m->d + 1) & ~1;
+    static int flush_tiles = -1;   // experiment knob: TCSDN_KNN_FLUSH = tiles between two evaluation rounds
+    if (flush_tiles < 0) { const char *e = getenv("TCSDN_KNN_FLUSH"); flush_tiles = e ? std::max(1, std::min(31, atoi(e))) : kEFlushTiles; }
+    A.flush_tiles = flush_tiles;
+    A.n_ref = (int)(svc ? m->n_sv : m->n_train);
     A.g2 = static_cast<float>(-m->gamma * 1.4426950408889634);
     const bool heap_smem = !svc && m->k <= kEHeapSmemK;
-    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 + (svc ? 0 : 512 * (size_t)kEListCap) +
-                        (heap_smem ? 512 * (size_t)kEHeapSmemK * 12 : 0);
+    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 +
+                        (svc ? 0 : 512 * (size_t)kEListCap * sizeof(uint16_t)) + (heap_smem ? 512 * (size_t)m->k * 12 : 0);
     const int64_t n_super = (n + kERows - 1) / kERows;
     const unsigned grid = (unsigned)std::min<int64_t>(n_super, m->sm_count);
 #define TCSDN_LAUNCH(SVCF, NC)                                                                                    \
