@@ -152,6 +152,16 @@ __device__ __forceinline__ void e_mma(uint32_t tmem_d, uint64_t da, uint64_t db,
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// exactly one lane of a converged warp gets true (the pattern the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool e_elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n.reg .b32 rx;\n.reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void e_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(e_smem(bar)) : "memory");
 }
@@ -168,6 +178,28 @@ __device__ __forceinline__ void e_tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 32-column TMEM load without the wait (several loads in flight); e_tmem_wait_ld() + e_regs_fence32() order the uses
+__device__ __forceinline__ void e_tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void e_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// emits nothing: tells the compiler that r[] is (re)defined here, so no use of it can be scheduled before the wait above
+__device__ __forceinline__ void e_regs_fence32(uint32_t (&r)[32]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 // 16-column TMEM load split into "issue" and "wait", so that the next chunk can be in flight while the current one is
 // processed.  The wait names the registers as in/out operands: the compiler must not touch them before it.
@@ -306,31 +338,40 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
         }
     } else if (warp == 17) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kEN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t g = 0, pass = 0;
-            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
-                e_mbar_wait(aFull, pass & 1);   // the 512 query rows of this pass are packed
+        // The whole warp runs this loop (warp-uniform control flow, so descriptors live in uniform registers) and ONE
+        // elected lane issues.  Issuing from `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma in an
+        // ELECT / BRA.U.ANY serialisation loop: 215 instructions per reference tile for 20 MMAs, on an issue port shared
+        // with four epilogue warps -- that, not the tensor pipe, was the engine's critical path (ncu, profiles/r01c).
+        // instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kEN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // shared-memory descriptor: K-major, SWIZZLE_NONE; high word = SBO(1280 B) >> 4 | version 1 << 14, low word =
+        // start >> 4 | LBO(128 B) >> 4 << 16; one K step of 16 advances the start by 256 B = 16 units
+        const uint64_t desc_hi = ((uint64_t)(kESBO >> 4) | ((uint64_t)1 << 14)) << 32;
+        const uint32_t a_lo = ((e_smem(sA) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+        uint32_t g = 0, pass = 0;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
+            e_mbar_wait(aFull, pass & 1);   // the 512 query rows of this pass are packed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                e_mbar_wait(&fullB[s], ph);
+                e_mbar_wait(&accEmpty[b], bph ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int j = 0; j < A.n_tiles; ++j, ++g) {
-                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
-                    const uint32_t b = g & 1, bph = (g >> 1) & 1;
-                    e_mbar_wait(&fullB[s], ph);
-                    e_mbar_wait(&accEmpty[b], bph ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t bBase = e_smem(sB + (size_t)s * A.tile_bytes);
+                if (e_elect_one()) {
+                    const uint32_t b_lo = ((e_smem(sB + (size_t)s * A.tile_bytes) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const uint32_t aBase = e_smem(sA + t * kEATile);
                         const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
 #pragma unroll
                         for (int k = 0; k < kEKSteps; ++k)
-                            e_mma(dcol, e_desc(aBase + k * 256), e_desc(bBase + k * 256), idesc, k > 0);
+                            e_mma(dcol, desc_hi | (uint64_t)(a_lo + (uint32_t)(t * (kEATile >> 4) + k * 16)),
+                                  desc_hi | (uint64_t)(b_lo + (uint32_t)(k * 16)), idesc, k > 0);
                     }
                     e_commit(&emptyB[s]);    // smem stage may be refilled once these MMAs have read it
                     e_commit(&accFull[b]);   // accumulators of this reference tile are complete
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -404,15 +445,14 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 unsigned long long n_exact = 0;
                 // candidate list entries: tile offset since the last round << 11 | group of 8 columns << 8 | pass mask
                 uint16_t *mylist = reinterpret_cast<uint16_t *>(cand) + (size_t)tid * kEListCap;
-                int cnt = 0, base_tile = 0;
+                int cnt = 0, base_tile = 0, next_round = 1;
                 const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(qt * 2 * kEN);
 #pragma unroll 1
                 for (int j = 0; j <= A.n_tiles; ++j) {
                     // ---- evaluation round: at the end, every `period` tiles (short while the threshold is still falling
                     // fast), or when a list could overflow in this tile
-                    const int period = min(A.flush_tiles, 1 + (j >> 2));
-                    const bool due = j == A.n_tiles || j - base_tile >= period;
-                    if (due || __any_sync(0xffffffffu, cnt > kEListCap - kEListRoom)) {
+                    const bool need = j >= next_round || cnt > kEListCap - kEListRoom;
+                    if (__any_sync(0xffffffffu, need)) {
                         int li = 0, gbase = 0;
                         uint32_t m = 0;
                         auto next = [&](int32_t &idx) -> bool {   // pops this thread's next candidate (training index order)
@@ -426,7 +466,12 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                             m &= m - 1;
                             return true;
                         };
-                        // two candidates per round: two independent fp64 chains and twelve 16-byte loads in flight
+                        // the query row is not kept in registers across the filter loop (it needs them for 64 accumulator
+                        // values): re-read it here, once per round of evaluations
+                        T qx[kEMaxD];
+#pragma unroll
+                        for (int jj = 0; jj < kEMaxD; ++jj) qx[jj] = (jj < A.d && live) ? X[row * A.d + jj] : static_cast<T>(0);
+                        // two candidates per pass: two independent fp64 chains and twelve 16-byte loads in flight
                         for (;;) {
                             int32_t ia = 0, ib = 0;   // (an idle slot reads row 0 and discards the result)
                             const bool pa = next(ia);
@@ -459,6 +504,8 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                         thr_base = knn_thr_base(hv0, qn);
                         cnt = 0;
                         base_tile = j;
+                        // next round: soon while the threshold is still falling fast, then every flush_tiles tiles
+                        next_round = min(A.n_tiles, j + min(A.flush_tiles, 1 + (j >> 2)));
                     }
                     if (j == A.n_tiles) break;
                     // ---- filter one reference tile: two halves of 32 accumulator columns (keeps 32, not 64, values live)
@@ -469,15 +516,22 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     const float thr = !live ? -FLT_MAX : (kAudit ? FLT_MAX : thr_base);
                     const uint32_t etile = (uint32_t)(j - base_tile) << 11;
                     uint32_t lp = e_smem(mylist) + 2u * (uint32_t)cnt;   // 32-bit shared address of the list's tail
+                    // all 64 accumulator values go to registers at once and the TMEM buffer is released right away: what a
+                    // warp then does with them (group visits, an evaluation round) no longer holds up the next tile's MMAs
+                    uint32_t r0[32], r1[32];
+                    e_tmem_ld32_issue(taddr0 + b * kEN, r0);
+                    e_tmem_ld32_issue(taddr0 + b * kEN + 32, r1);
+                    e_tmem_wait_ld();
+                    e_regs_fence32(r0);
+                    e_regs_fence32(r1);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         float v[32];
-                        e_tmem_ld32(taddr0 + b * kEN + h * 32, v);
-                        if (h == 1) {
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
-                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(h == 0 ? r0[i] : r1[i]);
                         // group minima first: two halves out of three hold nothing for any lane of the warp.  Padding
                         // columns carry +inf and never pass.
                         float gm[4];
