@@ -127,7 +127,7 @@ __device__ __forceinline__ void e_mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
         asm volatile(
             "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x2000;\n"   // suspend-time hint (ns): park, do not poll
             "selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(done)
             : "r"(e_smem(bar)), "r"(parity)

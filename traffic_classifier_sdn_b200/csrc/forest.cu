@@ -111,6 +111,70 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_
     }
 }
 
+// ---- the shared-memory walker.  While a group's nodes are copied into the tree buffer they are re-encoded so that a
+// step needs no masking of an index into an address and no leaf-flag test:
+//   y' = feature-or-class << 20 | (step * 8)      (steps are byte distances; a buffer holds < 2^17 nodes)
+//   x  unchanged; the HALT node becomes a pure leaf of a dummy class C whose step is 0: finished chains keep "adding"
+//   to an accumulator row nobody reads (acc has C + 1 rows), so pure leaf <=> x == -inf with no second test.
+// Per step: LDS.64 node, SHF feature, 2 IMAD (addresses of xs[f][r], acc[f][r]), LDS x, compare, predicated LDS/DADD/STS
+// for the leaf count, NaN test + branch for impure leaves, mask/select/add for the position: 15 instructions (the
+// index-based walker below needs 21).
+__device__ __forceinline__ uint2 to_compact(uint2 nd, int C) {
+    if (nd.x == kNegInf && nd.y == 0u) return make_uint2(kNegInf, (uint32_t)C << 20);          // halt
+    return make_uint2(nd.x, (((nd.y >> 24) & 0x7Fu) << 20) | ((nd.y & 0xFFFFFFu) << 3));
+}
+
+__device__ __forceinline__ void acc_add_one_if_s(uint32_t smem_addr, bool pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .f64 t;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "@p ld.shared.f64 t, [%0];\n"
+        "add.rn.f64 t, t, 0d3FF0000000000000;\n"   // unconditional: a predicated add makes ptxas emit DADD + 2 FSEL
+        "@p st.shared.f64 [%0], t;\n"
+        "}\n" ::"r"(smem_addr),
+        "r"((uint32_t)pred)
+        : "memory");
+}
+
+template <int kFThreads, int kRPT>
+__device__ __forceinline__ void walk_group_smem(uint32_t nodes_addr, uint32_t halt_addr, uint32_t xs_addr, uint32_t acc_addr,
+                                                double *acc, const double *leaf_val, int C, int r0, int nrows_live) {
+    uint32_t a[kRPT];
+#pragma unroll
+    for (int q = 0; q < kRPT; ++q) a[q] = (r0 + q * kFThreads) < nrows_live ? nodes_addr : halt_addr;
+    for (;;) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            uint2 nd[kRPT];
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q)
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nd[q].x), "=r"(nd[q].y) : "r"(a[q]));
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) {
+                const uint32_t r = (uint32_t)(r0 + q * kFThreads);
+                const uint32_t f = nd[q].y >> 20;                                   // feature (internal) / class (leaf)
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xs_addr + r * 4u + f * (kFRows * 4u)));
+                acc_add_one_if_s(acc_addr + r * 8u + f * (kFRows * 8u), nd[q].x == kNegInf);
+                if (nd[q].x > kNegInf) {                                            // impure leaf: NaN payload = table index
+                    const double *lv = leaf_val + (size_t)(nd[q].x & 0x3FFFFFu) * C;
+                    for (int c = 0; c < C; ++c) {
+                        double v = lv[c];
+                        if (v != 0.0) acc[c * kFRows + r] += v;  // x + 0.0 == x: skipping is exact
+                    }
+                }
+                a[q] += (x <= __uint_as_float(nd[q].x)) ? 8u : (nd[q].y & 0xFFFFFu);
+            }
+        }
+        bool done = true;
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) done &= (a[q] == halt_addr);
+        if (done) break;
+    }
+}
+
 template <typename T, int kFThreads, int kRPT>
 __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_constant__ ForestArgs A,
                                                               const T *__restrict__ X,
@@ -118,10 +182,13 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
                                                               double *__restrict__ proba, int32_t *flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int d = A.d, C = A.C;
-    const int xrows = d > C ? d : C;                                        // leaves read xs[class][row] (value unused)
-    float *xs = reinterpret_cast<float *>(smem_raw);                       // [max(d,C)][kFRows]
-    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)xrows * kFRows * 4);  // [C][kFRows]
-    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + (size_t)xrows * kFRows * 4 + (size_t)C * kFRows * 8);
+    const int xrows = d > C + 1 ? d : C + 1;                                // leaves read xs[class][row] (value unused)
+    float *xs = reinterpret_cast<float *>(smem_raw);                       // [max(d,C+1)][kFRows]
+    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)xrows * kFRows * 4);  // [C+1][kFRows], row C = halt's dummy class
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem_raw + (size_t)xrows * kFRows * 4 + (size_t)(C + 1) * kFRows * 8);
+    const uint32_t xs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
+    const uint32_t acc_addr = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
+    const uint32_t snodes_addr = static_cast<uint32_t>(__cvta_generic_to_shared(snodes));
     __shared__ int32_t s_tb[1];  // placeholder to keep static smem non-empty (tree_base is read from L1)
 
     const int tid = threadIdx.x;
@@ -130,7 +197,7 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
     const bool single = (A.n_groups == 1) && (A.tree_base[A.n_trees] + 1 <= A.node_cap);
     if (single) {
         const int nn = A.tree_base[A.n_trees] + 1;
-        for (int i = tid; i < nn; i += kFThreads) snodes[i] = A.nodes[i];
+        for (int i = tid; i < nn; i += kFThreads) snodes[i] = to_compact(A.nodes[i], C);
     }
     if (xrows > d)
         for (int i = tid; i < (xrows - d) * kFRows; i += kFThreads) xs[d * kFRows + i] = 0.f;
@@ -152,7 +219,7 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
                 r += dr; f += df;
                 if (f >= d) { f -= d; r += 1; }
             }
-            for (int i = tid; i < C * kFRows; i += kFThreads) acc[i] = 0.0;
+            for (int i = tid; i < (C + 1) * kFRows; i += kFThreads) acc[i] = 0.0;   // row C: the halt node's dummy class
         }
         for (int g = 0; g < A.n_groups; ++g) {
             const int t_begin = A.group_begin[g], t_end = A.group_begin[g + 1];
@@ -161,11 +228,12 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             const bool in_smem = gn <= A.node_cap;
             if (!single && in_smem) {
                 __syncthreads();  // everyone is done with the previous group's nodes
-                for (int i = tid; i < gn; i += kFThreads) snodes[i] = A.nodes[node0 + i];
+                for (int i = tid; i < gn; i += kFThreads) snodes[i] = to_compact(A.nodes[node0 + i], C);
             }
             __syncthreads();
             if (in_smem)
-                walk_group<true, kFThreads, kRPT>(snodes, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
+                walk_group_smem<kFThreads, kRPT>(snodes_addr, snodes_addr + (uint32_t)(gn - 1) * 8u, xs_addr, acc_addr, acc,
+                                                 A.leaf_val, C, tid, live);
             else
                 walk_group<false, kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
         }
@@ -201,7 +269,7 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
     if (d > 127 || C > 127) { set_error("forest: n_features and n_classes must be <= 127"); return TCSDN_EINVAL; }
     int dev_smem = 0;
     TCSDN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->dev));
-    const int64_t fixed = (int64_t)(d > C ? d : C) * kFRows * 4 + (int64_t)C * kFRows * 8 + 1024;
+    const int64_t fixed = (int64_t)(d > C + 1 ? d : C + 1) * kFRows * 4 + (int64_t)(C + 1) * kFRows * 8 + 1024;
     if (fixed + 8 * 64 > dev_smem) {
         set_error("forest: d=%d, n_classes=%d need %lld bytes of shared memory per tile (device has %d)", d, C,
                   (long long)fixed, dev_smem);
@@ -328,7 +396,7 @@ template <typename T, int kFThreads, int kRPT>
 static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
     static_assert(kFThreads * kRPT == kFRows, "tile geometry");
     auto kern = forest_kernel<T, kFThreads, kRPT>;
-    const int64_t fixed = (int64_t)(m->d > m->n_classes ? m->d : m->n_classes) * kFRows * 4 + (int64_t)m->n_classes * kFRows * 8;
+    const int64_t fixed = (int64_t)(m->d > m->n_classes + 1 ? m->d : m->n_classes + 1) * kFRows * 4 + (int64_t)(m->n_classes + 1) * kFRows * 8;
     int64_t buf_nodes = (m->max_group_nodes > 0 ? m->max_group_nodes : 0) + 1;   // largest in-smem group + its halt node
     if (buf_nodes < 64) buf_nodes = 64;
     const size_t smem = (size_t)fixed + (size_t)buf_nodes * 8;
