@@ -130,6 +130,23 @@ int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream);
 int tcsdn_svc_ovr_from_ovo(const double *dec, int64_t n, int32_t n_classes, int32_t loc, double *out,
                            void *cuda_stream);
 
+/* ---- multi-GPU: one process per GPU, rows sharded, models replicated ------------------
+ * predict() never communicates: rank r classifies its contiguous block of n_block = ceil(n / world) rows.  The only
+ * exchange the path can want -- the full label vector on every rank -- is ONE ncclAllGather of int32 indices.
+ * NCCL is bound at run time (dlopen libnccl.so.2); nothing else in the library needs it.
+ *   tcsdn_comm_unique_id   rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (any transport:
+ *                          the reference has none, bench/tests use torch.distributed's store)
+ *   tcsdn_comm_init        collective over all ranks; the calling thread's current CUDA device is the rank's GPU
+ *   tcsdn_allgather_labels local [n_local] (device, n_local <= n_block; the short last shard is padded with -1),
+ *                          all [world * n_block] (device); enqueued on `cuda_stream` */
+#define TCSDN_COMM_ID_BYTES 128
+typedef struct tcsdn_comm tcsdn_comm_t;
+int tcsdn_comm_unique_id(void *id_out);
+int tcsdn_comm_init(int32_t rank, int32_t world, const void *unique_id, tcsdn_comm_t **out);
+int tcsdn_allgather_labels(tcsdn_comm_t *comm, const int32_t *local, int64_t n_local, int64_t n_block, int32_t *all,
+                           void *cuda_stream);
+void tcsdn_comm_destroy(tcsdn_comm_t *comm);
+
 /* ---- N1 (next row): Flow.updateforward/updatereverse on device ----------------------------------
  * reference traffic_classifier.py:63-96,104.  One call applies one poll to n flows.
  * state [n][TCSDN_FLOW_STATE] float64 (device), layout per direction:

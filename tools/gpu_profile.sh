@@ -19,7 +19,11 @@ prof forest forest_kernel python bench.py --workload forest --no-extras --steps 
 prof forest_hbm forest_kernel python bench.py --workload forest_hbm --no-extras --steps 3 --warmup 3
 prof svc engine_kernel python tools/run_workload.py svc 10000000 4
 prof knn engine_kernel python tools/run_workload.py knn 10000000 4
+# per-instruction execution counts of the KNN engine kernel, grouped into regions (unit = one warp x one reference tile)
+python tools/ncu_sass_dump.py gpurun_out/prof_${TAG}_knn.ncu-rep gpurun_out/knn_sass_counts_${TAG}.txt
+mkdir -p gpurun_out/profiles
+python tools/sass_regions.py gpurun_out/knn_sass_counts_${TAG}.txt $((19532*782*16)) 2.0 > gpurun_out/profiles/${TAG}_knn_sass_regions.txt 2>&1
 # summarise on the box (only gpurun_out/ travels back, 64 MiB at most) and drop the bulky reports that are not needed again
 python tools/make_profile_summary.py ${TAG} gpurun_out/profiles > gpurun_out/summary_${TAG}.log 2>&1
-rm -f gpurun_out/prof_${TAG}_logistic.ncu-rep gpurun_out/prof_${TAG}_forest_hbm.ncu-rep gpurun_out/prof_${TAG}_gnb.ncu-rep
+rm -f gpurun_out/prof_${TAG}_*.ncu-rep
 du -sh gpurun_out

@@ -15,6 +15,7 @@ HOST, DEVICE = 0, 1
 OK, EINVAL, ECUDA, ENOMEM, ENONFINITE = 0, -1, -2, -3, -4
 OPT_ENGINE, OPT_CHUNK_ROWS, OPT_CHECK_FINITE = 1, 2, 3
 FLOW_STATE = 19
+COMM_ID_BYTES = 128
 
 _vp = C.c_void_p
 _f64p = C.POINTER(C.c_double)
@@ -46,6 +47,10 @@ SIGNATURES = {
     "tcsdn_sync_check": (C.c_int, [_vp, _vp]),
     "tcsdn_svc_ovr_from_ovo": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "tcsdn_flow_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32, _vp]),
+    "tcsdn_comm_unique_id": (C.c_int, [_vp]),
+    "tcsdn_comm_init": (C.c_int, [C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]),
+    "tcsdn_allgather_labels": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "tcsdn_comm_destroy": (None, [_vp]),
 }
 
 _lib = None

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtcsdn.so")
-SOURCES = ["abi.cu", "scorers.cu", "forest.cu", "knn.cu", "svc.cu", "flow.cu", "dist_engine.cu"]
+SOURCES = ["abi.cu", "scorers.cu", "forest.cu", "knn.cu", "svc.cu", "flow.cu", "dist_engine.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
     with open(os.path.join(objdir, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++", "-shared", "-o", LIB] + objs + ["-lcuda"]
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++", "-shared", "-o", LIB] + objs + ["-lcuda", "-ldl"]
     subprocess.check_call(cmd, env=env)
     if verbose:
         print("\n".join(log))

@@ -25,19 +25,19 @@
 //
 // Data layout.  create() packs the reference rows once into tile images of 64 rows x K=80 bf16 in the UMMA
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
-// followed by side data the epilogue needs: SVC the tile's dual coefficients [C-1][64] fp32 and centre, KNN the tile's
-// original fp64 rows (exact re-evaluation reads them from shared memory, not from L2).  A tile image is contiguous in HBM, so one
-// cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
-// boundaries (padded with zero-coefficient rows).
+// followed (SVC) by the tile's dual coefficients [C-1][64] fp32 and its centre.  A tile image is contiguous in HBM, so
+// one cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
+// boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows (even row
+// stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.
 //
 // Kernel (persistent, 1 CTA / SM, 576 threads).  A CTA owns 512 query rows at a time:
 //   warps 0-15  each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
 //               memory, same canonical layout), later reads its accumulator row from TMEM (tcgen05.ld 32x32b)
 //               and runs the KNN filter / SVC exp-and-accumulate epilogue on 64 columns per reference tile;
 //   warp 16     one lane streams reference tile images through a 4-stage ring (bulk copy + mbarrier tx count);
-//   warp 17     one lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per reference tile into a
-//               double-buffered TMEM accumulator (4 tiles x 2 buffers x 64 columns = all 512 columns) and
-//               commits to the ring's "empty" barrier and the accumulator's "full" barrier.
+//   warp 17     runs warp-uniformly; one ELECTED lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per
+//               reference tile into a double-buffered TMEM accumulator (4 tiles x 2 buffers x 64 columns = all 512
+//               columns) and commits to the ring's "empty" barrier and the accumulator's "full" barrier.
 // Each reference tile (10 KB) is reused by 512 query rows: 16 B/clk/SM of L2 traffic against 640 clk of MMA.
 //
 // A hazard worth writing down (it cost a debugging session on the B200): an mbarrier.arrive does NOT wait for the

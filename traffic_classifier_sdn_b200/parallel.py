@@ -9,7 +9,11 @@ One process per GPU (torchrun); ``torch.distributed`` is plumbing, the kernels n
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
+
+from . import _lib
 
 
 def shard_bounds(n: int, rank: int, world: int):
@@ -21,12 +25,53 @@ def shard_bounds(n: int, rank: int, world: int):
     return start, min(n, start + per)
 
 
-def predict_sharded(model, X, gather: bool = True, group=None):
+class Communicator:
+    """The library's own NCCL communicator (include/tcsdn.h: tcsdn_comm_init / tcsdn_allgather_labels).
+
+    Collective constructor: every rank of the ``torch.distributed`` group calls it; rank 0 creates the NCCL unique
+    id and the group's object broadcast carries it to the others (any transport would do -- the C ABI only wants
+    the 128 bytes).  The current CUDA device must already be this rank's GPU."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        if self.rank == 0:
+            _lib.check(self._lib.tcsdn_comm_unique_id(buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.tcsdn_comm_init(self.rank, self.world, C.c_char_p(box[0]), C.byref(self._h)))
+
+    def allgather_labels(self, local, n_block: int):
+        """local: CUDA int32 tensor with <= n_block entries -> CUDA int32 tensor [world * n_block] (short shards padded -1)."""
+        import torch
+        out = torch.empty(self.world * n_block, dtype=torch.int32, device=local.device)
+        st = torch.cuda.current_stream(local.device).cuda_stream
+        _lib.check(self._lib.tcsdn_allgather_labels(self._h, C.c_void_p(local.data_ptr() if local.numel() else 0),
+                                                    local.numel(), n_block, C.c_void_p(out.data_ptr()), C.c_void_p(st)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.tcsdn_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def predict_sharded(model, X, gather: bool = True, group=None, comm: "Communicator | None" = None):
     """Classify this rank's block of X (every rank holds the same X, or at least its own block's rows).
 
     Returns the int32 class indices of the whole batch on every rank when ``gather`` (one all-gather of the
     per-rank label vectors, padded to equal length), else only this rank's block.  Works with numpy arrays
-    (gloo) and CUDA tensors (NCCL)."""
+    (gloo) and CUDA tensors (NCCL: through ``comm`` -- the library's own communicator -- when one is passed,
+    else through torch.distributed)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
@@ -39,6 +84,8 @@ def predict_sharded(model, X, gather: bool = True, group=None):
     if not gather:
         return local
     per = -(-n // world)
+    if comm is not None and torch.is_tensor(local) and local.is_cuda:
+        return comm.allgather_labels(local.contiguous(), per)[:n]
     is_t = torch.is_tensor(local)
     t = local if is_t else torch.from_numpy(np.ascontiguousarray(local))
     pad = torch.zeros(per, dtype=torch.int32, device=t.device)   # equal-sized contributions for the collective
