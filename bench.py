@@ -203,6 +203,39 @@ def max_over_ranks(x, world, device):
     return float(t.item())
 
 
+def measure_with_gather(w, steps, world, device):
+    """SURVEY 8(e) asks for the N-GPU number with and without the gather: the same per-GPU step followed by ONE
+    all-gather of every rank's int32 labels through the library's communicator (tcsdn_allgather_labels)."""
+    import torch
+    from traffic_classifier_sdn_b200 import from_spec
+    from traffic_classifier_sdn_b200.parallel import Communicator
+    est = from_spec(w["spec"])
+    rows, d = w["rows"], w["d"]
+    rank = dist_env()[0]
+    x = synth_rows(rows, d, seed=4000 + rank, device=device)
+    lab = torch.empty(rows, dtype=torch.int32, device=device)
+    comm = Communicator()
+    for _ in range(3):
+        est.predict_indices(x, out=lab)
+        allv = comm.allgather_labels(lab, rows)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        est.predict_indices(x, out=lab)
+        allv = comm.allgather_labels(lab, rows)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world, device)
+    assert allv.numel() == rows * world
+    comm.close()
+    return {"value": rows * world * steps / (ms * 1e-3), "unit": "flow-rows/s", "ms_per_step": ms / steps,
+            "gathered_bytes_per_step": 4 * rows * world, "how": "eager launches (no CUDA graph): predict + ncclAllGather per step"}
+
+
 def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, clock_probe_s=0.0):
     """Device-resident timing (`value`) + end-to-end timing (`e2e`) of one workload on this rank."""
     import torch
@@ -425,6 +458,7 @@ def main():
                 models[name] = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = cpu_reference(w, max_seconds=15.0) if (rank == 0 and world == 1) else None
+    gathered = measure_with_gather(w, args.steps, world, device) if world > 1 else None
     if rank == 0:
         line = {"metric": "flow-rows/sec classified (GaussianNB, 1M x 8 synthetic flow rows per GPU)"
                 if args.workload == "gnb" else f"flow-rows/sec classified ({args.workload})",
@@ -438,6 +472,8 @@ def main():
                 "roofline": head["roofline"], "kernel_ms": head["kernel_ms"], "clocks": clocks, "models": models}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gathered is not None:
+            line["with_label_allgather"] = gathered
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

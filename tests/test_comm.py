@@ -1,0 +1,61 @@
+"""The multi-GPU C ABI (include/tcsdn.h: tcsdn_comm_*): argument checking on CPU, a world-size-1 all-gather and --
+when the box has two GPUs -- the two-rank torchrun check on the GPU."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from traffic_classifier_sdn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_comm_argument_errors_need_no_gpu():
+    lib = _lib.load()
+    h = C.c_void_p()
+    ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    assert lib.tcsdn_comm_init(2, 2, ident, C.byref(h)) == _lib.EINVAL      # rank out of range
+    assert lib.tcsdn_comm_init(0, 0, ident, C.byref(h)) == _lib.EINVAL      # empty world
+    assert lib.tcsdn_comm_init(0, 1, None, C.byref(h)) == _lib.EINVAL       # no id
+    assert lib.tcsdn_comm_unique_id(None) == _lib.EINVAL
+    assert lib.tcsdn_allgather_labels(None, None, 0, 0, None, None) == _lib.EINVAL
+    assert b"allgather_labels" in lib.tcsdn_last_error()
+    lib.tcsdn_comm_destroy(None)   # no-op
+
+
+@pytest.mark.gpu
+def test_comm_world1_allgather_pads_short_shard():
+    import torch
+    lib = _lib.load()
+    ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    _lib.check(lib.tcsdn_comm_unique_id(ident))
+    h = C.c_void_p()
+    torch.cuda.set_device(0)
+    _lib.check(lib.tcsdn_comm_init(0, 1, ident, C.byref(h)))
+    try:
+        local = torch.arange(1000, dtype=torch.int32, device="cuda")
+        out = torch.full((1024,), 7, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.tcsdn_allgather_labels(h, C.c_void_p(local.data_ptr()), 1000, 1024, C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(st)))
+        _lib.check(lib.tcsdn_allgather_labels(h, C.c_void_p(local.data_ptr()), 1000, 1000, C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(st)))   # full shard: no staging copy
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:1000], np.arange(1000)) and np.all(got[1000:] == -1)
+    finally:
+        lib.tcsdn_comm_destroy(h)
+
+
+@pytest.mark.gpu
+def test_two_rank_sharded_predict_and_gather():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tools", "two_gpu_gather.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "gather ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

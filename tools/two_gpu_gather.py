@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Row-sharded predict + the library's NCCL all-gather on W GPUs (run under torchrun; W = WORLD_SIZE).
+Every rank classifies its block, gathers all labels through tcsdn_allgather_labels, and checks them against a
+full single-GPU predict of the same rows.  Prints 'gather ok' on rank 0."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from traffic_classifier_sdn_b200 import from_spec, synth
+from traffic_classifier_sdn_b200.parallel import Communicator, predict_sharded
+import bench
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+comm = Communicator()
+ok = True
+for name, n in (("gnb", 1_000_003), ("forest", 200_001), ("gnb", 5)):
+    w = bench.build_workload(name)
+    est = from_spec(w["spec"])
+    X = bench.synth_rows(n, w["d"], seed=77, device=dev)
+    full = est.predict_indices(X)
+    got = predict_sharded(est, X, gather=True, comm=comm)
+    got_torch = predict_sharded(est, X, gather=True)            # torch.distributed path, same answer
+    mine = predict_sharded(est, X, gather=False)
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(full, got)) and bool(torch.equal(full, got_torch)) and got.numel() == n
+    per = -(-n // world)
+    ok &= bool(torch.equal(mine, full[min(n, rank * per):min(n, (rank + 1) * per)]))
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+comm.close()
+if rank == 0:
+    print("gather ok" if int(flag.item()) == 1 else "gather MISMATCH", "world", world)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
