@@ -130,6 +130,24 @@ int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream);
 int tcsdn_svc_ovr_from_ovo(const double *dec, int64_t n, int32_t n_classes, int32_t loc, double *out,
                            void *cuda_stream);
 
+/* ---- N3 (next row): `.fit` of the two cheap models on the GPU -------------------------------------
+ * (the other four estimators keep importing fitted parameters from scikit-learn).  X [n][d] float32/float64 and
+ * y / labels_out live where `loc` says; the small outputs (theta, var, ..., centers_out) are HOST arrays.
+ * Sums are fp64 and deterministic but not in numpy's order: results agree with scikit-learn to ~1e-13 relative.
+ *
+ * tcsdn_gnb_fit     GaussianNB.fit (sk:naive_bayes.py:385-476): y [n] class index in [0, n_classes);
+ *                   theta/var [n_classes][d] (var includes epsilon = var_smoothing * max_j Var(X_j)),
+ *                   class_prior [n_classes], class_count (nullable) [n_classes], epsilon (nullable).
+ * tcsdn_kmeans_fit  KMeans(init=init_centers, n_init=1, algorithm="lloyd").fit (sk:cluster/_kmeans.py:620-760):
+ *                   E-step fused with the M-step's sums per iteration; stops on unchanged labels or on
+ *                   sum(center_shift^2) <= mean(Var(X_j)) * tol.  k <= 33.  labels_out (nullable) [n]. */
+int tcsdn_gnb_fit(const void *x, const int32_t *y, int64_t n, int32_t d, int32_t n_classes, int32_t x_dtype,
+                  int32_t loc, double var_smoothing, double *theta, double *var, double *class_prior,
+                  double *class_count, double *epsilon, void *cuda_stream);
+int tcsdn_kmeans_fit(const void *x, int64_t n, int32_t d, int32_t k, int32_t x_dtype, int32_t loc,
+                     const double *init_centers, int32_t max_iter, double tol, double *centers_out,
+                     int32_t *labels_out, double *inertia_out, int32_t *n_iter_out, void *cuda_stream);
+
 /* ---- multi-GPU: one process per GPU, rows sharded, models replicated ------------------
  * predict() never communicates: rank r classifies its contiguous block of n_block = ceil(n / world) rows.  The only
  * exchange the path can want -- the full label vector on every rank -- is ONE ncclAllGather of int32 indices.

@@ -179,3 +179,46 @@ def test_engine_nonfinite_rows_raise(specs):
     for kind in ("knn", "svc"):
         with pytest.raises(ValueError, match="NaN|infinity"):
             from_spec(specs[kind]).predict(X)
+
+
+# ------------------------------------------------------------------ BASELINE sizes: 10M query rows (configs[2], configs[3])
+@pytest.mark.parametrize("name", ["knn", "svc"])
+def test_engine_full_size_properties(name):
+    """The bench workloads at their full size (10M rows x 50k training rows / 20k support vectors), checked through
+    properties that do not need a 10M-row oracle: a permutation of the rows permutes the labels, one launch equals
+    eight slices, a strided sample equals the CPU oracle and the fp64 CUDA-core kernel (KNN: exactly; SVC: wherever no
+    pairwise decision value is within the engine tolerance of zero), and the exact-evaluation counter stays sane."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    w = bench.build_workload(name)
+    n = w["full_rows"]
+    est = from_spec(w["spec"])
+    X = bench.synth_rows(n, w["d"], seed=4242, device=torch.device("cuda", 0))
+    full = est.predict_indices(X)
+    st = est.stats()
+    assert st[1] == n and st[2] == 0                       # every row went through the tensor-core engine
+    g = torch.Generator(device="cpu").manual_seed(3)
+    perm = torch.randperm(n, generator=g).cuda()
+    assert torch.equal(full[perm], est.predict_indices(X[perm].contiguous()))
+    assert torch.equal(full, torch.cat([est.predict_indices(c.contiguous()) for c in X.chunk(8)]))
+    est.sync_check()
+    hist = np.bincount(full.cpu().numpy(), minlength=8)
+    assert hist.sum() == n and (hist > 0).sum() >= 2       # not a constant answer
+    # strided sample against the oracle (fp64 restatement of sklearn) and the fp64 kernel
+    s = slice(0, n, 20_011)
+    xs = X[s].cpu().numpy().astype(np.float64)
+    lab_o, sc_o = oracle.predict(w["spec"], xs, want_scores=True)
+    lab_e = full[s].cpu().numpy()
+    est64 = _force(from_spec(w["spec"]), 1)
+    lab_k = est64.predict_indices(xs)
+    assert np.array_equal(lab_k, lab_o)
+    if name == "knn":
+        assert np.array_equal(lab_e, lab_o)
+        evals_per_query = (est.stats()[3]) / (3.0 * n)     # three full passes so far
+        assert 5 <= evals_per_query < 400
+    else:
+        safe = np.abs(sc_o).min(axis=1) > SVC_ENGINE_TOL
+        assert np.array_equal(lab_e[safe], lab_o[safe]) and (~safe).mean() < 0.02

@@ -95,8 +95,13 @@ class _Base:
     def _sk_estimator(self):
         raise NotImplementedError
 
-    def fit(self, X, y=None):
-        """Train with scikit-learn on the host, then move the fitted parameters to HBM."""
+    def fit(self, X, y=None, backend="auto"):
+        """Train, then move the fitted parameters to HBM.  GaussianNB and KMeans fit on the GPU (SURVEY row N3,
+        csrc/fit.cu) unless ``backend="sklearn"``; the other four train with scikit-learn on the host."""
+        if backend not in ("auto", "gpu", "sklearn"):
+            raise ValueError("backend must be 'auto', 'gpu' or 'sklearn'")
+        if backend != "sklearn" and self._fit_gpu(X, y, strict=backend == "gpu"):
+            return self
         est = self._sk_estimator()
         est.fit(X) if y is None and self._kind == "kmeans" else est.fit(X, y)
         self._adopt(modelio.spec_from_estimator(est))
@@ -104,6 +109,27 @@ class _Base:
             if hasattr(est, attr):
                 setattr(self, attr, getattr(est, attr))
         return self
+
+    def _fit_gpu(self, X, y, strict):
+        """-> True when the GPU fitted the model.  Estimators without a GPU fit return False (or raise if strict)."""
+        if strict:
+            raise ValueError(f"{type(self).__name__} has no GPU fit: it trains with scikit-learn on the host")
+        return False
+
+    @staticmethod
+    def _fit_rows(X):
+        """-> (pointer, n, d, dtype code, loc code, keepalive) for a fit call: numpy rows or a CUDA torch tensor."""
+        if _is_torch_cuda(X):
+            t = X.contiguous()
+            if t.dim() != 2 or str(t.dtype) not in ("torch.float32", "torch.float64"):
+                raise ValueError("expected a 2-D float32/float64 CUDA tensor")
+            return C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], _lib.F32 if str(t.dtype) == "torch.float32" else _lib.F64, \
+                _lib.DEVICE, t
+        a = np.asarray(X)
+        if a.ndim != 2:
+            raise ValueError(f"Expected 2D array, got {a.ndim}D array instead")
+        a = np.ascontiguousarray(a, dtype=np.float32 if a.dtype == np.float32 else np.float64)
+        return _p(a, C.c_void_p), a.shape[0], a.shape[1], _lib.F32 if a.dtype == np.float32 else _lib.F64, _lib.HOST, a
 
     def _adopt(self, spec):
         if spec["kind"] != self._kind:
@@ -260,6 +286,37 @@ class GaussianNB(_Base):
         _lib.check(lib.tcsdn_gnb_create(_p(th, _lib._f64p), _p(var, _lib._f64p), _p(pr, _lib._f64p), th.shape[0],
                                         th.shape[1], C.byref(h)))
 
+    def _fit_gpu(self, X, y, strict):
+        """GaussianNB.fit on the GPU (tcsdn_gnb_fit): per-class mean/variance, epsilon_, priors."""
+        p = self._params
+        if p.get("priors") is not None or y is None:
+            if strict:
+                raise ValueError("the GPU fit supports priors=None and needs y")
+            return False
+        if _is_torch_cuda(y):
+            y = y.cpu().numpy()
+        classes, yi = np.unique(np.asarray(y), return_inverse=True)
+        ptr, n, d, dt, loc, keep = self._fit_rows(X)
+        if len(yi) != n:
+            raise ValueError(f"Found input variables with inconsistent numbers of samples: [{n}, {len(yi)}]")
+        yi = np.ascontiguousarray(yi, np.int32)
+        ydev = None
+        if loc == _lib.DEVICE:
+            import torch
+            ydev = torch.from_numpy(yi).to(keep.device)
+            yptr = C.c_void_p(ydev.data_ptr())
+        else:
+            yptr = _p(yi, C.c_void_p)
+        Cn = len(classes)
+        th, var = np.empty((Cn, d)), np.empty((Cn, d))
+        pr, cnt, eps = np.empty(Cn), np.empty(Cn), C.c_double(0.0)
+        f = _lib._f64p
+        _lib.check(_lib.load().tcsdn_gnb_fit(ptr, yptr, n, d, Cn, dt, loc, float(p.get("var_smoothing", 1e-9)), _p(th, f),
+                                             _p(var, f), _p(pr, f), _p(cnt, f), C.byref(eps), None))
+        self._adopt(dict(kind="gnb", theta=th, var=var, class_prior=pr, classes=classes, n_features=d))
+        self.class_count_, self.epsilon_ = cnt, float(eps.value)
+        return True
+
     def _joint_log_likelihood(self, X):
         return self._scores(X)
 
@@ -290,6 +347,51 @@ class KMeans(_Base):
 
     def _labels_from_indices(self, idx):
         return idx.astype(np.int32, copy=False)
+
+    def _fit_gpu(self, X, y, strict):
+        """Lloyd iterations on the GPU (tcsdn_kmeans_fit) from ONE set of initial centres: an ``init`` array, or
+        scikit-learn's k-means++ seeding run on the host with this estimator's ``random_state`` (the same centres
+        ``sklearn.cluster.KMeans(n_init=1)`` starts from).  Several restarts (n_init > 1) stay with scikit-learn."""
+        p = self._params
+        k = int(p.get("n_clusters", 8))
+        init = p.get("init", "k-means++")
+        n_init = p.get("n_init", "auto")
+        ok = (isinstance(init, np.ndarray) or init == "k-means++") and n_init in ("auto", 1) and \
+            p.get("algorithm", "lloyd") == "lloyd" and k <= 33
+        if not ok:
+            if strict:
+                raise ValueError("the GPU fit supports init=array or 'k-means++', n_init in ('auto', 1), algorithm='lloyd', "
+                                 "n_clusters <= 33")
+            return False
+        ptr, n, d, dt, loc, keep = self._fit_rows(X)
+        if isinstance(init, np.ndarray):
+            c0 = np.ascontiguousarray(init, np.float64)
+            if c0.shape != (k, d):
+                raise ValueError(f"The shape of the initial centers {c0.shape} does not match the number of clusters {k} "
+                                 f"and features {d}.")
+        else:
+            from sklearn.cluster import kmeans_plusplus
+            from sklearn.utils import check_random_state
+            host = keep.cpu().numpy() if loc == _lib.DEVICE else keep
+            host = np.asarray(host, np.float64)
+            mean = host.mean(axis=0)                      # sklearn seeds on the mean-centred rows
+            c0, _ = kmeans_plusplus(host - mean, k, random_state=check_random_state(p.get("random_state")))
+            c0 = np.ascontiguousarray(c0 + mean, np.float64)
+        ctr = np.empty((k, d))
+        inertia, n_iter = C.c_double(0.0), C.c_int32(0)
+        labels = None
+        lptr = None
+        if loc == _lib.HOST:
+            labels = np.empty(n, np.int32)
+            lptr = _p(labels, C.c_void_p)
+        _lib.check(_lib.load().tcsdn_kmeans_fit(ptr, n, d, k, dt, loc, _p(c0, _lib._f64p), int(p.get("max_iter", 300)),
+                                                float(p.get("tol", 1e-4)), _p(ctr, _lib._f64p), lptr, C.byref(inertia),
+                                                C.byref(n_iter), None))
+        self._adopt(dict(kind="kmeans", centers=ctr, classes=np.arange(k, dtype=np.int32), n_features=d))
+        self.inertia_, self.n_iter_ = float(inertia.value), int(n_iter.value)
+        if labels is not None:
+            self.labels_ = labels
+        return True
 
     def fit_predict(self, X, y=None):
         return self.fit(X).predict(X)
