@@ -55,7 +55,8 @@ enum { /* tcsdn_model_kind() */
 };
 
 enum { /* tcsdn_set_option() keys */
-    TCSDN_OPT_ENGINE = 1,      /* 0 auto, 1 force the fp64 CUDA-core kernels, 2 force the tensor-core engine,
+    TCSDN_OPT_ENGINE = 1,      /* 0 auto, 1 force the fp64 CUDA-core kernels (knn/svc; GaussianNB: no fp32 pre-pass),
+                                  2 force the tensor-core engine,
                                   3 engine in audit mode (knn filter off, error statistic on; tests only) */
     TCSDN_OPT_CHUNK_ROWS = 2,  /* host-pointer pipeline chunk (rows); 0 = default */
     TCSDN_OPT_CHECK_FINITE = 3 /* 1 (default): fail with TCSDN_ENONFINITE on NaN/inf input */
@@ -113,8 +114,9 @@ int tcsdn_model_score_cols(const tcsdn_model_t *m);
 int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value);
 /* counters of the last predict on this handle: [0] kernels launched, [1] rows through the tensor-core
  * engine, [2] rows through the fp64 CUDA-core kernels, [3] exact fp64 re-evaluations of the knn filter (cumulative
- * since create), [5] largest observed |tensor-core distance - exact| / (||x||^2+||t||^2), times 2^40 (cumulative);
- * rest reserved.  out has 8 slots.  Reading the engine counters synchronises the device. */
+ * since create), [5] largest observed |tensor-core distance - exact| / (||x||^2+||t||^2), times 2^40 (cumulative),
+ * [6] GaussianNB rows the certified fp32 pre-pass handed to the fp64 definition (cumulative since create);
+ * rest reserved.  out has 8 slots.  Reading the device-side counters synchronises the device. */
 int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
 
 /* ---- the hot call: one model.predict(X)  (traffic_classifier.py:106) ---------------------------- */

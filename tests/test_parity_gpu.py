@@ -378,3 +378,36 @@ def test_cli_replays_a_monitor_log_through_the_gpu(tmp_path, golden, specs, caps
         final_table = out[out.rstrip().rfind("Flow ID"):]
         got = [row.split("|")[4].strip() for row in final_table.splitlines() if row.startswith("|") and "Flow ID" not in row]
         assert got == exp, (word, got, exp)   # --every 1: the last report is printed at the last data line = final state
+
+
+# ------------------------------------------------------------------ GaussianNB: certified fp32 pre-pass
+def test_gnb_fp32_prepass_is_certified_or_refined(specs, models):
+    """float32 rows, labels only: the kernel evaluates in fp32 with an error bound and re-runs uncertified rows in fp64.
+    Labels must equal the fp64 kernel's on every row -- bulk rows, exact ties and near-ties -- and the counter of
+    refined rows (stats[6]) must show that both routes were taken."""
+    import torch
+    from traffic_classifier_sdn_b200 import _lib
+    n = 1_000_000
+    X = torch.from_numpy(synth.make_flows(n, seed=123, dtype=np.float32, return_labels=False)).cuda()
+    fast = from_spec(specs["gnb"])
+    slow = from_spec(specs["gnb"])
+    slow.set_option(_lib.OPT_ENGINE, 1)                       # fp64 only
+    a, b = fast.predict_indices(X), slow.predict_indices(X)
+    assert torch.equal(a, b)
+    refined = int(fast.stats()[6])
+    assert int(slow.stats()[6]) == 0 and refined < 0.05 * n   # the pre-pass certifies the bulk
+    print(f"gnb pre-pass: {refined} of {n} rows refined in fp64")
+    # exact ties (two identical classes) and near ties (class 2 = class 0 shifted by a few ulps of fp32)
+    d, rng = 8, np.random.default_rng(5)
+    theta = rng.uniform(1.0, 1e4, (3, d))
+    theta[1] = theta[0]
+    theta[2] = theta[0] * (1.0 + 3e-8)
+    var = np.tile(rng.uniform(1.0, 1e3, (1, d)), (3, 1))
+    spec = dict(kind="gnb", theta=theta, var=var, class_prior=np.full(3, 1 / 3), classes=np.arange(3), n_features=d)
+    Xt = (theta[0] + rng.normal(0, 30.0, (200_000, d))).astype(np.float32)
+    est = from_spec(spec)
+    got = est.predict_indices(torch.from_numpy(Xt).cuda()).cpu().numpy()
+    ref = oracle.predict(spec, Xt.astype(np.float64), want_scores=False)[0]
+    assert np.array_equal(got, ref)
+    assert int(est.stats()[6]) > 0.5 * len(Xt)                # nothing here can be certified in fp32
+    assert set(np.unique(ref)) <= {0, 2}                      # class 1 never beats its identical twin (first maximum)

@@ -173,8 +173,23 @@ static int scorer_common(tcsdn_model *m, const std::vector<double> &a, const std
                 m->sp.b[r * d + j] = b[(size_t)r * d + j];
             }
             m->sp.c[r] = c[r];
+            double k = std::fabs(c[r]);
+            for (int j = 0; j < d; ++j) {
+                m->sp.af[r * d + j] = static_cast<float>(a[(size_t)r * d + j]);
+                m->sp.bf[r * d + j] = static_cast<float>(b[(size_t)r * d + j]);
+                k += b[(size_t)r * d + j] * b[(size_t)r * d + j];
+            }
+            m->sp.cf[r] = static_cast<float>(c[r]);
+            // kf = 2^-19 (c~ + |c| + sum b^2), rounded up: the constant part of the error bound as the pre-pass uses it
+            // (E = eps (c~ - acc~) + eps (|c| + sum b^2); c~ + |c| >= 0 keeps the formula one-signed)
+            const double ke = (static_cast<double>(m->sp.cf[r]) + k) / 524288.0;
+            float kf = static_cast<float>(ke);
+            if (static_cast<double>(kf) < ke) kf = std::nextafterf(kf, INFINITY);
+            m->sp.kf[r] = std::nextafterf(kf, INFINITY);
         }
         m->sp_valid = true;
+        unsigned long long zero = 0;
+        TCSDN_TRY(upload(&m->d_refined, &zero, 1));
     }
     return TCSDN_OK;
 }
@@ -330,6 +345,7 @@ void tcsdn_destroy(tcsdn_model_t *m) {
     cudaFree(m->d_sv); cudaFree(m->d_coef); cudaFree(m->d_rho); cudaFree(m->d_start);
     cudaFree(m->d_nodes); cudaFree(m->d_tree_base); cudaFree(m->d_group_begin); cudaFree(m->d_leaf_val);
     cudaFree(m->d_flag);
+    cudaFree(m->d_refined);
     if (prev >= 0) cudaSetDevice(prev);
     delete m;
 }
@@ -357,6 +373,10 @@ int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out) {
     if (!m || !out) { set_error("NULL argument"); return TCSDN_EINVAL; }
     for (int i = 0; i < 8; ++i) out[i] = m->stats[i];
     if (m->engine) engine_read_stats(m, &out[3], &out[5]);   // cumulative since create(); synchronises the device
+    if (m->d_refined) {   // cumulative since create(); synchronises the device
+        unsigned long long v = 0;
+        if (cudaMemcpy(&v, m->d_refined, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) out[6] = (int64_t)v;
+    }
     return TCSDN_OK;
 }
 

@@ -43,6 +43,12 @@ struct ScorerParams {
     double a[kMaxClassesFast * 16];
     double b[kMaxClassesFast * 16];
     double c[kMaxClassesFast];
+    // GaussianNB fp32 pre-pass (scorers.cu): the same constants rounded to fp32, and per class the constant part of
+    // the error bound, |c| + sum_j b^2 (rounded up)
+    float af[kMaxClassesFast * 16];
+    float bf[kMaxClassesFast * 16];
+    float cf[kMaxClassesFast];
+    float kf[kMaxClassesFast];
 };
 
 struct DeviceBuf {
@@ -107,6 +113,7 @@ struct tcsdn_model {
 
     // ---- per-handle misc
     int32_t *d_flag = nullptr;       // device error flag (non-finite input)
+    unsigned long long *d_refined = nullptr;   // GaussianNB: rows the fp32 pre-pass could not certify (re-run in fp64)
     std::mutex mu;
     std::vector<tcsdn::Workspace *> pool;
     void *engine = nullptr;          // tensor-core engine state (dist_engine.cu), may be null

@@ -125,11 +125,64 @@ __device__ __forceinline__ void score_rows(const ScorerParams &P, const double (
     }
 }
 
+// GaussianNB labels from an fp32 pre-pass with a rigorous error bound; rows it cannot certify are re-run in fp64 by
+// the caller, so the labels are those of the fp64 definition, always.  (The kernel was fp64-pipe-bound: 96 DFMA per
+// row at 64/clk/SM is 5.3 us per 1M rows, as long as the HBM transfer it should hide behind.)
+//   fp64 definition   t = x a - b,  jll_c = c_c - sum_j t^2        (one rounding per fma, 2^-53: negligible here)
+//   fp32 pre-pass     the same with a, b, c rounded to fp32 and fp32 fma: t~, acc~
+//   |t~ - t| <= 2^-24 (|x a| + |b| + |t~|) <= 2^-23 (|t~| + |b|)          since |x a| + |b| <= |t| + 2 |b|
+//   |t~^2 - t^2| <= 2^-22 (1.5 t~^2 + 0.5 b^2);   d <= 16 accumulation roundings <= 2^-20 (|c| + T),  T = sum_j t~^2
+//   => |acc~_c - jll_c| <= E_c = 2^-19 (T_c + |c_c| + sum_j b_cj^2)       (1.45x slack), with T_c = c~_c - acc~_c for free
+// A row is certified when  acc~_best - E_best > acc~_c + E_c  for every other class: then jll_best > jll_c strictly, the
+// fp64 argmax is `best` and no tie rule is involved.  NaN/inf anywhere fails the comparison and lands in the fp64 path.
+template <int D, int R, int kRPT>
+__device__ __forceinline__ void gnb_prepass_rows(const ScorerParams &P, const float (&x)[kRPT][D], int (&arg)[kRPT],
+                                                 bool (&sure)[kRPT]) {
+    // hi/lo = acc -/+ E with E = eps (c + k - acc):  hi = acc (1 - eps) + eps (c + k),  lo = acc (1 + eps) - eps (c + k): one
+    // fma each (their own rounding, 2^-24 |acc|, is 1/32 of E: inside the slack).  The class with the largest hi is the
+    // only one that can be certified, and it is iff its lo beats every other hi.
+    constexpr float kEps = 1.0f / 524288.0f;   // 2^-19
+    float best_lo[kRPT], best_hi[kRPT], others_hi[kRPT];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float acc[kRPT];
+        const float c = P.cf[r];
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) acc[q] = c;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float ca = P.af[r * D + j], cb = -P.bf[r * D + j];
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) {
+                const float t = fmaf(x[q][j], ca, cb);
+                acc[q] = fmaf(-t, t, acc[q]);
+            }
+        }
+        const float ke = P.kf[r];   // eps (c + k), rounded up
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) {
+            const float hi = fmaf(acc[q], 1.0f - kEps, ke), lo = fmaf(acc[q], 1.0f + kEps, -ke);
+            if (r == 0) {
+                best_lo[q] = lo; best_hi[q] = hi; others_hi[q] = -INFINITY; arg[q] = 0;
+            } else {
+                const bool gt = hi > best_hi[q];
+                others_hi[q] = fmaxf(others_hi[q], gt ? best_hi[q] : hi);
+                best_hi[q] = fmaxf(best_hi[q], hi);
+                best_lo[q] = gt ? lo : best_lo[q];
+                arg[q] = gt ? r : arg[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kRPT; ++q) sure[q] = best_lo[q] > others_hi[q];   // false for NaN / -inf
+}
+
 template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
 __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
                                                                 const T *__restrict__ X, int64_t n,
                                                                 int32_t *__restrict__ labels,
-                                                                double *__restrict__ scores, int32_t *flag) {
+                                                                double *__restrict__ scores, int32_t *flag,
+                                                                unsigned long long *refined) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kTile = kThreads * kRPT;
     constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
@@ -173,6 +226,48 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
         mbar_wait(&full[stage], parity);
         const int64_t row0 = tile * kTile;
         const T *tp = reinterpret_cast<const T *>(reinterpret_cast<unsigned char *>(tiles) + (size_t)stage * kTileBytes);
+        if constexpr (KIND == KIND_GNB && sizeof(T) == 4) {
+            if (refined != nullptr) {   // labels only, fp32 rows: certified fp32 pre-pass (see gnb_prepass_rows)
+                float xf[kRPT][D];
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q) {
+                    const bool in = row0 + q * kThreads + tid < n;
+                    const float *rowp = reinterpret_cast<const float *>(tp) + (q * kThreads + tid) * D;
+#pragma unroll
+                    for (int v = 0; v < D / 4; ++v) {
+                        const float4 u = in ? *reinterpret_cast<const float4 *>(rowp + v * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xf[q][v * 4 + 0] = u.x; xf[q][v * 4 + 1] = u.y; xf[q][v * 4 + 2] = u.z; xf[q][v * 4 + 3] = u.w;
+                        nf = fmaf(u.x, 0.f, nf); nf = fmaf(u.y, 0.f, nf); nf = fmaf(u.z, 0.f, nf); nf = fmaf(u.w, 0.f, nf);
+                    }
+                }
+                __threadfence_block();
+                __syncthreads();
+                if (tid == 0) {
+                    int64_t nt = tile + (int64_t)kStages * stride;
+                    if (nt < n_tiles) issue(nt, stage);
+                }
+                int arg[kRPT];
+                bool sure[kRPT];
+                gnb_prepass_rows<D, R, kRPT>(P, xf, arg, sure);
+                unsigned redo = 0;
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q) {
+                    if (!sure[q]) {   // rare: this row's top-2 margin is inside the fp32 error bound -> the fp64 definition decides
+                        double xd[1][D], s1[1][R];
+                        int a1[1];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) xd[0][j] = static_cast<double>(xf[q][j]);
+                        score_rows<D, R, KIND, 1>(P, xd, s1, a1);
+                        arg[q] = a1[0];
+                        ++redo;
+                    }
+                    const int64_t row = row0 + q * kThreads + tid;
+                    if (row < n) labels[row] = arg[q];
+                }
+                if (redo) atomicAdd(refined, (unsigned long long)redo);
+                continue;
+            }
+        }
         double x[kRPT][D];
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {   // thread t owns rows t, t+128, t+256, t+384 of the tile (conflict-free 16 B loads)
@@ -261,7 +356,11 @@ static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labe
     // (Programmatic dependent launch was tried here -- griddepcontrol.wait/launch_dependents with the PDL launch
     // attribute -- and made the 1M-row CUDA-graph step slower, 15.1 vs 11.9 us: early-launched CTAs of the next grid
     // sit on the SMs waiting.  Plain launches it is.)
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag);
+    // fp32 pre-pass: GaussianNB, float32 rows, labels only, unless the fp64 kernels are forced (TCSDN_OPT_ENGINE = 1)
+    static int prepass = -1;   // experiment knob: TCSDN_GNB_PREPASS=0 keeps the tiled kernel on its fp64 path
+    if (prepass < 0) { const char *e = getenv("TCSDN_GNB_PREPASS"); prepass = e ? atoi(e) : 1; }
+    unsigned long long *refined = (KIND == KIND_GNB && sizeof(T) == 4 && scores == nullptr && prepass) ? m->d_refined : nullptr;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag, refined);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
 }
