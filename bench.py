@@ -373,6 +373,27 @@ def cpu_reference(w, max_seconds=20.0, threads=None):
                        f"{cores} host threads available (n_jobs=-1 where the estimator has it)")
 
 
+def per_row_call_pattern(w, est, seconds=1.0):
+    """The reference's literal call pattern (traffic_classifier.py:103-106): model.predict([[12 floats]]) once per flow.
+    Calls per second of scikit-learn's estimator and of this package's estimator (one-row host call: H2D, kernel, D2H)."""
+    import warnings
+    rows = synth_rows(256, w["d"], seed=77).numpy().astype(np.float64).tolist()
+    out = {"what": "model.predict([[d floats]]) once per flow, as traffic_classifier.py:103-106 does"}
+    for name, model in (("sklearn_calls_per_s", sklearn_model(w)), ("gpu_calls_per_s", est)):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model.predict([rows[0]])
+                t0, k = time.perf_counter(), 0
+                while time.perf_counter() - t0 < seconds:
+                    model.predict([rows[k % len(rows)]])
+                    k += 1
+                out[name] = k / (time.perf_counter() - t0)
+        except Exception as exc:
+            out[name] = f"{type(exc).__name__}: {exc}"
+    return out
+
+
 def load_traffic(name):
     """DRAM bytes per launch of the workload's dominant kernel, from the committed ncu capture (profiles/)."""
     best = None
@@ -463,6 +484,7 @@ def main():
                 models[name] = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = cpu_reference(w, max_seconds=15.0) if (rank == 0 and world == 1) else None
+    call_pattern = per_row_call_pattern(w, head["est"]) if (rank == 0 and world == 1) else None
     gathered = measure_with_gather(w, args.steps, world, device) if world > 1 else None
     if rank == 0:
         line = {"metric": "flow-rows/sec classified (GaussianNB, 1M x 8 synthetic flow rows per GPU)"
@@ -477,6 +499,8 @@ def main():
                 "roofline": head["roofline"], "kernel_ms": head["kernel_ms"], "clocks": clocks, "models": models}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if call_pattern is not None:
+            line["reference_call_pattern"] = call_pattern
         if gathered is not None:
             line["with_label_allgather"] = gathered
         print(json.dumps(line))
