@@ -1,9 +1,9 @@
 #!/bin/bash
-# forest check: parity tests, then both forest workloads
+# forest check: parity tests, then both forest workloads with and without the coherence sort
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -q -x -k "forest or Forest" > gpurun_out/pytest_forest.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -q -x -k "forest or Forest or golden or ragged or large_batch" > gpurun_out/pytest_forest.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/pytest_forest.log
-for w in forest forest_hbm; do
-  timeout 300 python bench.py --workload $w --no-extras --steps 10 --warmup 3 > gpurun_out/forest_$w.json 2>/dev/null
-  python tools/show_bench.py gpurun_out/forest_$w.json | head -1
-done
+for s in 1 0; do for w in forest forest_hbm; do
+  TCSDN_FOREST_SORT=$s timeout 300 python bench.py --workload $w --no-extras --steps 10 --warmup 3 > gpurun_out/forest_${s}_$w.json 2>/dev/null
+  echo "sort=$s $w: $(python tools/show_bench.py gpurun_out/forest_${s}_$w.json | head -1)"
+done; done

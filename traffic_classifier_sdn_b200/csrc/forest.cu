@@ -42,6 +42,7 @@ struct ForestArgs {
     const double *leaf_val;
     int n_trees, n_groups, d, C;
     int node_cap;                // nodes in the smem tree buffer
+    int sort;                    // re-assign rows to threads in tree-0 leaf order (coherence sort)
     int64_t n;
 };
 
@@ -75,11 +76,11 @@ __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
 
 template <bool IN_SMEM, int kFThreads, int kRPT>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_t halt, const float *xs, double *acc,
-                                           const double *leaf_val, int C, int r0, int nrows_live) {
+                                           const double *leaf_val, int C, int r0, const bool (&alive)[kRPT]) {
     uint32_t pos[kRPT];
     const uint32_t acc_base = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
 #pragma unroll
-    for (int q = 0; q < kRPT; ++q) pos[q] = (r0 + q * kFThreads) < nrows_live ? 0u : halt;
+    for (int q = 0; q < kRPT; ++q) pos[q] = alive[q] ? 0u : halt;
     for (;;) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -140,10 +141,11 @@ __device__ __forceinline__ void acc_add_one_if_s(uint32_t smem_addr, bool pred) 
 
 template <int kFThreads, int kRPT>
 __device__ __forceinline__ void walk_group_smem(uint32_t nodes_addr, uint32_t halt_addr, uint32_t xs_addr, uint32_t acc_addr,
-                                                double *acc, const double *leaf_val, int C, int r0, int nrows_live) {
+                                                double *acc, const double *leaf_val, int C, int r0,
+                                                const bool (&alive)[kRPT]) {
     uint32_t a[kRPT];
 #pragma unroll
-    for (int q = 0; q < kRPT; ++q) a[q] = (r0 + q * kFThreads) < nrows_live ? nodes_addr : halt_addr;
+    for (int q = 0; q < kRPT; ++q) a[q] = alive[q] ? nodes_addr : halt_addr;
     for (;;) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -190,6 +192,8 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
     const uint32_t acc_addr = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
     const uint32_t snodes_addr = static_cast<uint32_t>(__cvta_generic_to_shared(snodes));
     __shared__ int32_t s_tb[1];  // placeholder to keep static smem non-empty (tree_base is read from L1)
+    __shared__ int s_hist[kFRows];          // coherence sort: bucket counts / cursors
+    __shared__ uint16_t s_orig[kFRows];     // coherence sort: slot -> row of the tile
 
     const int tid = threadIdx.x;
     const int64_t n_tiles = (A.n + kFRows - 1) / kFRows;
@@ -221,6 +225,79 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             }
             for (int i = tid; i < (C + 1) * kFRows; i += kFThreads) acc[i] = 0.0;   // row C: the halt node's dummy class
         }
+        // ---- coherence sort.  The walk is bound by shared-memory wavefronts: 32 lanes at 32 different nodes cost ~6
+        // wavefronts per node fetch, lanes at the SAME node cost one.  Rows that end in the same leaf of tree 0 are similar
+        // and mostly take the same branches in the other trees too, so the tile's rows are re-assigned to threads in the
+        // order of their tree-0 leaf (preorder position, 1024 buckets, counting sort).  Which thread walks a row changes
+        // nothing about that row's arithmetic: results go back to the row's original index.
+        int orig[kRPT];
+        bool alive[kRPT];
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) { orig[q] = tid + q * kFThreads; alive[q] = orig[q] < live; }
+        if (A.sort) {
+            __syncthreads();   // xs staged, acc zeroed
+            int key[kRPT];
+            const uint32_t n0 = (uint32_t)A.tree_base[1];
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) {
+                key[q] = kFRows - 1;
+                if (alive[q]) {   // walk tree 0 in place (wide encoding, L2): a few dozen loads per row, once per tile
+                    uint32_t pos = 0;
+                    for (;;) {
+                        const uint2 nd = A.nodes[pos];
+                        if (nd.y & kLeaf) break;
+                        const float x = xs[((nd.y >> 24) & 0x7Fu) * kFRows + orig[q]];
+                        pos += (x <= __uint_as_float(nd.x)) ? 1u : (nd.y & 0xFFFFFFu);
+                    }
+                    key[q] = (int)(((uint64_t)pos * kFRows) / n0);
+                }
+            }
+            for (int i = tid; i < kFRows; i += kFThreads) s_hist[i] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) atomicAdd(&s_hist[key[q]], 1);
+            __syncthreads();
+            if (tid < 32) {   // exclusive prefix sum over 1024 buckets: 32 per lane, then a warp scan of the lane totals
+                int run = 0;
+                for (int i = 0; i < kFRows / 32; ++i) run += s_hist[tid * (kFRows / 32) + i];
+                int inc = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= o) inc += v;
+                }
+                int base = inc - run;
+                for (int i = 0; i < kFRows / 32; ++i) {
+                    const int c = s_hist[tid * (kFRows / 32) + i];
+                    s_hist[tid * (kFRows / 32) + i] = base;
+                    base += c;
+                }
+            }
+            __syncthreads();
+            int dst[kRPT];
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) dst[q] = atomicAdd(&s_hist[key[q]], 1);   // any order inside a bucket will do
+            // move the columns of xs: slot dst[q] receives the row that sat in slot tid + q * kFThreads
+            for (int f0 = 0; f0 < d; f0 += 8) {
+                float v[kRPT][8];
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q)
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) v[q][f] = (f0 + f < d) ? xs[(f0 + f) * kFRows + tid + q * kFThreads] : 0.f;
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < kRPT; ++q)
+#pragma unroll
+                    for (int f = 0; f < 8; ++f)
+                        if (f0 + f < d) xs[(f0 + f) * kFRows + dst[q]] = v[q][f];
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) s_orig[dst[q]] = (uint16_t)(tid + q * kFThreads);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kRPT; ++q) { orig[q] = s_orig[tid + q * kFThreads]; alive[q] = orig[q] < live; }
+        }
         for (int g = 0; g < A.n_groups; ++g) {
             const int t_begin = A.group_begin[g], t_end = A.group_begin[g + 1];
             const int node0 = A.tree_base[t_begin] + g;                   // g halt nodes precede this group
@@ -233,24 +310,24 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             __syncthreads();
             if (in_smem)
                 walk_group_smem<kFThreads, kRPT>(snodes_addr, snodes_addr + (uint32_t)(gn - 1) * 8u, xs_addr, acc_addr, acc,
-                                                 A.leaf_val, C, tid, live);
+                                                 A.leaf_val, C, tid, alive);
             else
-                walk_group<false, kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, live);
+                walk_group<false, kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, alive);
         }
         // each thread finalises its own rows (only it touched their accumulators)
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {
-            const int r = tid + q * kFThreads;
-            if (r >= live) continue;
+            const int r = tid + q * kFThreads;   // the slot this thread walked; orig[q] = the row of the tile it holds
+            if (!alive[q]) continue;
             int arg = 0;
             double best = 0.0;
             const double nt = (double)A.n_trees;
             for (int c = 0; c < C; ++c) {
                 double p = acc[c * kFRows + r] / nt;
-                if (proba) proba[(row0 + r) * C + c] = p;
+                if (proba) proba[(row0 + orig[q]) * C + c] = p;
                 if (c == 0 || p > best) { best = p; arg = c; }
             }
-            labels[row0 + r] = arg;
+            labels[row0 + orig[q]] = arg;
         }
     }
     if (flag && nf != nf) atomicOr(flag, 1);
@@ -269,7 +346,7 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
     if (d > 127 || C > 127) { set_error("forest: n_features and n_classes must be <= 127"); return TCSDN_EINVAL; }
     int dev_smem = 0;
     TCSDN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->dev));
-    const int64_t fixed = (int64_t)(d > C + 1 ? d : C + 1) * kFRows * 4 + (int64_t)(C + 1) * kFRows * 8 + 1024;
+    const int64_t fixed = (int64_t)(d > C + 1 ? d : C + 1) * kFRows * 4 + (int64_t)(C + 1) * kFRows * 8 + 1024 + 6 * 1024 + 64;
     if (fixed + 8 * 64 > dev_smem) {
         set_error("forest: d=%d, n_classes=%d need %lld bytes of shared memory per tile (device has %d)", d, C,
                   (long long)fixed, dev_smem);
@@ -405,6 +482,9 @@ static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *lab
     A.nodes = m->d_nodes; A.tree_base = m->d_tree_base; A.group_begin = m->d_group_begin;
     A.leaf_val = m->d_leaf_val; A.n_trees = m->n_trees; A.n_groups = m->n_groups; A.d = m->d;
     A.C = m->n_classes; A.node_cap = (int)buf_nodes; A.n = n;
+    static int sort = -1;   // experiment knob: TCSDN_FOREST_SORT=0 walks the rows in their original order
+    if (sort < 0) { const char *e = getenv("TCSDN_FOREST_SORT"); sort = e ? atoi(e) : 1; }
+    A.sort = sort && m->n_trees > 1;
     int64_t tiles = (n + kFRows - 1) / kFRows;
     int64_t grid = tiles < m->sm_count ? tiles : m->sm_count;
     kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, m->opt_check_finite ? m->d_flag : nullptr);
