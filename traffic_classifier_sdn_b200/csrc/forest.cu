@@ -9,10 +9,11 @@
 // Data layout.  Every tree is re-laid in preorder so that the left child is always the next node; a
 // node is 8 bytes:  x = threshold as float32, rounded DOWN from sklearn's float64 threshold
 // (for a float32 feature value v:  (double)v <= t  <=>  v <= floor32(t), so the compare is bit-exact
-// in fp32);  y = feature << 24 | distance to the right child.  Leaves set y's top bit and keep in x the
-// position of the next tree's root; a pure leaf (one class fraction == 1.0) carries its class in y, an
-// impure leaf indexes a table of fp64 fraction vectors kept in HBM (see walk_group for the bit layout).  Trees are packed, in estimator order, into groups that fit the shared
-// memory tree buffer.
+// in fp32);  y = feature << 24 | distance to the right child.  Leaves set y's top bit and keep in y's low 24 bits the
+// distance to the next tree's root; a pure leaf (one class fraction == 1.0) has x = -inf and its class in y, an impure
+// leaf has a NaN x whose payload indexes a table of fp64 fraction vectors kept in HBM (see walk_group for the bit
+// layout).  Trees are packed, in estimator order, into groups that fit the shared-memory tree buffer; while a group
+// is copied there its nodes are re-encoded for the fast walker (byte steps, see walk_group_smem).
 //
 // Kernel.  A CTA (1024 threads, one row each) owns a tile of 1024 rows: the tile is staged transposed in shared memory
 // (xs[f][row]: every lane reads its own bank whatever feature its node tests), per-row fp64
@@ -20,7 +21,9 @@
 // into the tree buffer once per tile.  A thread walks its row through the group's trees one
 // tree after another without re-converging with its neighbours (a lane that reaches a leaf starts
 // the next tree at once), adding each tree's fractions to its accumulators in tree order -- the
-// same fp64 addition sequence as sklearn's `out += proba`, hence identical bits.
+// same fp64 addition sequence as sklearn's `out += proba`, hence identical bits.  Before the walk the tile's rows
+// are re-assigned to threads in the order of their tree-0 leaf (coherence sort, see the kernel): the walk is bound by
+// shared-memory wavefronts, and lanes that sit at the same node share one.
 // Trees larger than the buffer are walked in place in HBM/L2.
 // Algorithmic bytes per row: 4*d in + 4 out (+ 8 per node visit).
 #include <cmath>
@@ -74,6 +77,7 @@ __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
         : "memory");
 }
 
+// the index-based walker: trees that do not fit the shared-memory buffer are walked where they lie (HBM / L2)
 template <bool IN_SMEM, int kFThreads, int kRPT>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_t halt, const float *xs, double *acc,
                                            const double *leaf_val, int C, int r0, const bool (&alive)[kRPT]) {
