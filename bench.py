@@ -99,7 +99,8 @@ def _build_workload(name, quick=False):
         Xtr, ytr = synth.make_flows(50_000, seed=seed + 2)
         spec = dict(kind="knn", fit_X=Xtr, y=ytr.astype(np.int32), k=5, classes=synth.CLASSES, n_features=12)
         return dict(spec=spec, sk=None, d=12, rows=10_000_000 if not quick else 200_000, bytes_per_row=52,
-                    flops_per_row=2 * 12 * 50_000, desc="KNeighbors k=5 brute force, 10M queries x 50k train rows "
+                    flops_per_row=2 * 12 * 50_000, issued_mma_flops_per_row=2 * 80 * 64 * ((50_000 + 63) // 64),
+                    desc="KNeighbors k=5 brute force, 10M queries x 50k train rows "
                     "(BASELINE configs[2])", bound="tensor", cpu_sample_rows=20_000)
     if name == "svc":
         rng = np.random.default_rng(seed + 3)
@@ -114,7 +115,9 @@ def _build_workload(name, quick=False):
                     gamma=float(gamma), classes=synth.CLASSES, n_features=12, decision_function_shape="ovr",
                     break_ties=False, n_classes=C)
         return dict(spec=spec, sk=None, d=12, rows=10_000_000 if not quick else 200_000, bytes_per_row=52,
-                    flops_per_row=2 * 12 * nsv + 2 * (C - 1) * nsv, desc="SVC(rbf) 10M flows x 20k support vectors, "
+                    flops_per_row=2 * 12 * nsv + 2 * (C - 1) * nsv,
+                    issued_mma_flops_per_row=2 * 80 * 64 * int(sum((int(c) + 63) // 64 for c in nsup)),   # classes padded to tiles
+                    desc="SVC(rbf) 10M flows x 20k support vectors, "
                     "6 classes (BASELINE configs[3])", bound="tensor", cpu_sample_rows=4_000)
     raise ValueError(name)
 
@@ -334,13 +337,18 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     if tr is not None:
         # the capture was taken on the full-size workload; scale if this run uses another batch size (--quick)
         tr = dict(tr, bytes=tr["bytes"] * rows / w["full_rows"])
+    roofline = dict(bound=w["bound"], achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
+                    traffic=None if tr is None else tr["bytes"], traffic_source=None if tr is None else tr["source"],
+                    peak_source=peaks["source"])
+    if w["bound"] == "tensor":
+        # next to the algorithmic flops, the flops the tensor cores are actually ISSUED (bf16 x 3 split:
+        # K = 80 per pair instead of d = 12, reference rows padded to 64-row tiles) and the ncu tensor-pipe figure
+        issued = rows * w["issued_mma_flops_per_row"] / (kernel_ms * 1e-3) / 1e12
+        roofline.update(issued_mma=issued, issued_mma_frac=issued / peak, tensor_pipe_pct_ncu=load_summary_field(w["name"], "tensor_pipe_pct"))
     return dict(value=value, ms_per_step=ms / steps, kernel_ms=kernel_ms, rows=rows, ring=ring, mode=mode, traffic=tr,
                 launches_per_step=launches_per_step, load_window=load_window,
                 e2e=dict(value=e2e, unit="flow-rows/s", h2d_bytes_per_step=rows * row_bytes, d2h_bytes_per_step=rows * 4),
-                roofline=dict(bound=w["bound"], achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
-                              traffic=None if tr is None else tr["bytes"], traffic_source=None if tr is None else tr["source"],
-                              peak_source=peaks["source"]),
-                est=est, batch0=batches[0])
+                roofline=roofline, est=est, batch0=batches[0])
 
 
 def cpu_reference(w, max_seconds=20.0, threads=None):
@@ -404,6 +412,19 @@ def load_traffic(name):
                 j = json.load(open(os.path.join(pdir, f)))
                 if name in j and j[name].get("dram_bytes"):
                     best = {"bytes": j[name]["dram_bytes"], "source": f"profiles/{f}"}
+    return best
+
+
+def load_summary_field(name, field):
+    """Latest committed ncu summary's value of `field` for the workload (profiles/*_ncu_summary.json), or None."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for f in sorted(os.listdir(pdir)):
+            if f.endswith("_ncu_summary.json"):
+                j = json.load(open(os.path.join(pdir, f)))
+                if name in j and j[name].get(field) is not None:
+                    best = j[name][field]
     return best
 
 
