@@ -281,6 +281,13 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     torch.cuda.synchronize()
+    try:
+        # a short busy-wait kernel goes first, so that the replay below is already queued on the device when the first
+        # event fires: the timed region then holds K steps of GPU work, not the host's graph-launch latency (which would
+        # otherwise weigh on a K = 5 run of 10 us steps far more than on a K = 20 run)
+        torch.cuda._sleep(400_000)
+    except Exception:
+        pass
     ev0.record()
     if graph is not None:
         graph.replay()
