@@ -513,7 +513,12 @@ def main():
 
     cpu = cpu_reference(w, max_seconds=15.0) if (rank == 0 and world == 1) else None
     call_pattern = per_row_call_pattern(w, head["est"]) if (rank == 0 and world == 1) else None
-    gathered = measure_with_gather(w, args.steps, world, device) if world > 1 else None
+    gathered = None
+    if world > 1:
+        try:
+            gathered = measure_with_gather(w, args.steps, world, device)
+        except Exception as exc:   # the headline line must survive a failure of this extra
+            gathered = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         line = {"metric": "flow-rows/sec classified (GaussianNB, 1M x 8 synthetic flow rows per GPU)"
                 if args.workload == "gnb" else f"flow-rows/sec classified ({args.workload})",
