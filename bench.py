@@ -383,9 +383,18 @@ def cpu_reference(w, max_seconds=20.0, threads=None):
             t0 = time.perf_counter()
             sk.predict(X)
             best = min(best, time.perf_counter() - t0)
-    return dict(value=n / best, unit="flow-rows/s", cores=cores, kind="reference",
-                sample=f"sklearn {type(sk).__name__}.predict on {n} of the workload's rows, best of 2, "
-                       f"{cores} host threads available (n_jobs=-1 where the estimator has it)")
+    out = dict(value=n / best, unit="flow-rows/s", cores=cores, kind="reference",
+               sample=f"sklearn {type(sk).__name__}.predict on {n} of the workload's rows, best of 2, "
+                      f"{cores} host threads available (n_jobs=-1 where the estimator has it)")
+    if w["spec"]["kind"] == "forest":
+        # the traversal accounting needs the MEASURED mean number of node visits per row (V-bar)
+        try:
+            m = min(n, 2000)
+            out["node_visits_per_row"] = float(sk.decision_path(X[:m])[0].nnz) / m
+        except Exception as exc:
+            out["node_visits_per_row"] = None
+            out["node_visits_error"] = f"{type(exc).__name__}: {exc}"
+    return out
 
 
 def per_row_call_pattern(w, est, seconds=1.0):
@@ -505,6 +514,11 @@ def main():
                          "gpu_launches_per_step": r["launches_per_step"], "engine_stats": r["est"].stats().tolist()}
                 if rank == 0 and world == 1:
                     entry["cpu_baseline"] = cpu_reference(wx, max_seconds=8.0)
+                    vbar = entry["cpu_baseline"].get("node_visits_per_row")
+                    if vbar:   # forest: rows/s x (52 + 8 V-bar) next to the compulsory-bytes figure
+                        tb = r["value"] * (wx["bytes_per_row"] + 8.0 * vbar) / 1e9
+                        entry["roofline"].update(traversal_bytes_per_row=wx["bytes_per_row"] + 8.0 * vbar, traversal_achieved=tb,
+                                                 traversal_frac=tb / peaks["hbm_gbs"])
                 models[name] = entry
                 del r
                 torch.cuda.empty_cache()
