@@ -361,7 +361,6 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
 def cpu_reference(w, max_seconds=20.0, threads=None):
     """scikit-learn predict on the host cores, on a bounded sample of the workload's rows."""
     import warnings
-    from threadpoolctl import threadpool_limits
     sk = sklearn_model(w)
     n = min(w["cpu_sample_rows"], w["rows"])
     X = synth_rows(n, w["d"], seed=1000).numpy()

@@ -7,7 +7,6 @@ Bars: class indices bit-exact everywhere; RandomForest probabilities and KNN vot
 KMeans scores <= 1e-11 of the row's largest score (fp64, FMA vs
 numpy association); SVC decision values <= 1e-9 absolute with the fp64 kernel.
 """
-import ctypes as C
 
 import numpy as np
 import pytest

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from traffic_classifier_sdn_b200 import from_spec, _lib
+from traffic_classifier_sdn_b200 import from_spec
 w = bench.build_workload("gnb")
 for rows in (1_000_000, 50_000_000):
     X = bench.synth_rows(rows, w["d"], seed=1000, device=torch.device("cuda", 0))

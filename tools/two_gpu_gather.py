@@ -6,7 +6,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from traffic_classifier_sdn_b200 import from_spec, synth
+from traffic_classifier_sdn_b200 import from_spec
 from traffic_classifier_sdn_b200.parallel import Communicator, predict_sharded
 import bench
 
