@@ -19,7 +19,9 @@
  *   - nothing here throws, aborts or calls exit().  There is no CPU fallback: without a CUDA device
  *     every create/predict fails with TCSDN_ECUDA.
  *   - handles are immutable after create; predict on one handle from several host threads is safe
- *     (per-call scratch comes from a mutex-guarded pool inside the handle).
+ *     (per-call scratch, including the non-finite flag of a host-pointer call, comes from a mutex-guarded pool
+ *     inside the handle; device-pointer calls share the handle's sticky flag, see tcsdn_sync_check).  A predict
+ *     runs on the handle's device and restores the caller's current device before it returns.
  *   - rows are row-major, contiguous [n][d], float32 or float64, in host or device memory.
  *     labels_out has n int32.  scores_out (nullable) has n*tcsdn_model_score_cols() float64 and
  *     lives where X lives.  With device pointers the call only enqueues work on `stream`; with host
@@ -56,10 +58,18 @@ enum { /* tcsdn_model_kind() */
 
 enum { /* tcsdn_set_option() keys */
     TCSDN_OPT_ENGINE = 1,      /* 0 auto, 1 force the fp64 CUDA-core kernels (knn/svc; GaussianNB: no fp32 pre-pass),
-                                  2 force the tensor-core engine,
-                                  3 engine in audit mode (knn filter off, error statistic on; tests only) */
+                                  2 force the tensor-core engine (svc: for label-only calls; decision values always come
+                                    from the fp64 kernel),
+                                  3 engine in audit mode, tests only (knn: filter off; svc: scores_out receives the engine's
+                                    uncorrected decision values; both: tensor-core error statistic in stats[5]),
+                                  4 svc engine, tests only: scores_out receives the certificate's per-pair error bounds */
     TCSDN_OPT_CHUNK_ROWS = 2,  /* host-pointer pipeline chunk (rows); 0 = default */
-    TCSDN_OPT_CHECK_FINITE = 3 /* 1 (default): fail with TCSDN_ENONFINITE on NaN/inf input */
+    TCSDN_OPT_CHECK_FINITE = 3, /* 1 (default): fail with TCSDN_ENONFINITE on NaN/inf input */
+    /* measurement knobs (defaults are the measured best; tools/gpu_check.sh sweeps them) */
+    TCSDN_OPT_SCORER_SHAPE = 4,    /* streaming scorers' CTA shape: 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2 */
+    TCSDN_OPT_FOREST_SHAPE = 5,    /* forest CTA shape: 0 = 1024 threads x 1 row, 1 = 512 x 2, 2 = 256 x 4 */
+    TCSDN_OPT_FOREST_SORT = 6,     /* 1 (default): re-assign a tile's rows to threads in tree-0 leaf order */
+    TCSDN_OPT_KNN_FLUSH_TILES = 7  /* knn engine: reference tiles between two exact-evaluation rounds, 1..31; 0 = default */
 };
 
 int tcsdn_version(void);
@@ -114,9 +124,10 @@ int tcsdn_model_score_cols(const tcsdn_model_t *m);
 int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value);
 /* counters of the last predict on this handle: [0] kernels launched, [1] rows through the tensor-core
  * engine, [2] rows through the fp64 CUDA-core kernels, [3] exact fp64 re-evaluations of the knn filter (cumulative
- * since create), [5] largest observed |tensor-core distance - exact| / (||x||^2+||t||^2), times 2^40 (cumulative),
- * [6] GaussianNB rows the certified fp32 pre-pass handed to the fp64 definition (cumulative since create);
- * rest reserved.  out has 8 slots.  Reading the device-side counters synchronises the device. */
+ * since create), [5] largest observed |tensor-core value - exact| / (the error model's denominator), times 2^40
+ * (cumulative, audit mode), [6] rows a certified fast path could not decide and handed to the fp64 definition
+ * (GaussianNB fp32 pre-pass, svc engine; cumulative since create); rest reserved.  out has 8 slots.  Reading the
+ * device-side counters synchronises the device.  Concurrent predicts on one handle add up in [0..2]. */
 int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
 
 /* ---- the hot call: one model.predict(X)  (traffic_classifier.py:106) ---------------------------- */
@@ -158,13 +169,20 @@ int tcsdn_kmeans_fit(const void *x, int64_t n, int32_t d, int32_t k, int32_t x_d
  *                          the reference has none, bench/tests use torch.distributed's store)
  *   tcsdn_comm_init        collective over all ranks; the calling thread's current CUDA device is the rank's GPU
  *   tcsdn_allgather_labels local [n_local] (device, n_local <= n_block; the short last shard is padded with -1),
- *                          all [world * n_block] (device); enqueued on `cuda_stream` */
+ *                          all [world * n_block] (device); enqueued on `cuda_stream`
+ *   tcsdn_allgather_labels_u8  same arguments and result plus the model's class count: with n_classes <= 255 the
+ *                          labels travel as one byte each (a quarter of the payload); pack, gather and unpack are
+ *                          enqueued on `cuda_stream` without host synchronisation, so predict + gather can be
+ *                          captured into one CUDA graph (make the first call with a new n_block outside the capture:
+ *                          it allocates the staging buffer) */
 #define TCSDN_COMM_ID_BYTES 128
 typedef struct tcsdn_comm tcsdn_comm_t;
 int tcsdn_comm_unique_id(void *id_out);
 int tcsdn_comm_init(int32_t rank, int32_t world, const void *unique_id, tcsdn_comm_t **out);
 int tcsdn_allgather_labels(tcsdn_comm_t *comm, const int32_t *local, int64_t n_local, int64_t n_block, int32_t *all,
                            void *cuda_stream);
+int tcsdn_allgather_labels_u8(tcsdn_comm_t *comm, const int32_t *local, int64_t n_local, int64_t n_block, int32_t *all,
+                              int32_t n_classes, void *cuda_stream);
 void tcsdn_comm_destroy(tcsdn_comm_t *comm);
 
 /* ---- N1 (next row): Flow.updateforward/updatereverse on device ----------------------------------

@@ -182,3 +182,27 @@ def test_cli_words(capsys):
     assert "specify traffic type" in capsys.readouterr().out
     assert cli.ALIASES["supervised"] == "logistic" and cli.ALIASES["unsupervised"] == "kmeans"
     assert set(modelio.MODEL_FILES) >= {"logistic", "kmeans", "svm", "kneighbors", "Randomforest", "gaussiannb"}
+
+
+def test_logistic_proba_forms_match_sklearn():
+    """multinomial -> softmax, binary -> sigmoid (sk:linear_model/_logistic.py:1620-1625), one-vs-rest models ->
+    normalised sigmoids (sk:linear_model/_base.py:429-451); the spec records which one the model uses."""
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.multiclass import OneVsRestClassifier
+    from traffic_classifier_sdn_b200.estimators import lr_proba
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(300, 5)); y = rng.integers(0, 4, 300)
+    sk = LogisticRegression(max_iter=200).fit(X, y)
+    spec = modelio.spec_from_estimator(sk)
+    assert spec["ovr"] is False
+    assert np.allclose(lr_proba(sk.decision_function(X), False), sk.predict_proba(X), rtol=0, atol=1e-15)
+    skb = LogisticRegression().fit(X, y % 2)
+    assert np.allclose(lr_proba(skb.decision_function(X)[:, None], False), skb.predict_proba(X), rtol=0, atol=1e-15)
+    # a one-vs-rest model: scikit-learn's own formula, reached through LinearClassifierMixin._predict_proba_lr
+    ovr = OneVsRestClassifier(LogisticRegression()).fit(X, y)
+    dec = np.column_stack([e.decision_function(X) for e in ovr.estimators_])
+    sk.coef_ = np.vstack([e.coef_ for e in ovr.estimators_]); sk.intercept_ = np.concatenate([e.intercept_ for e in ovr.estimators_])
+    assert np.allclose(lr_proba(dec.copy(), True), sk._predict_proba_lr(X), rtol=0, atol=1e-15)
+    sk.multi_class = "ovr"            # attribute of scikit-learn <= 1.6 estimators (the reference's pickles are 1.0.1)
+    assert modelio.spec_from_estimator(sk)["ovr"] is True
+    assert np.allclose(lr_proba(np.full((2, 3), -1e4), True), 1.0 / 3)   # all-zero sigmoids -> uniform

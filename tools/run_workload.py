@@ -8,6 +8,9 @@ from traffic_classifier_sdn_b200 import from_spec
 name, rows = sys.argv[1], int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 w = bench.build_workload(name)
 est = from_spec(w["spec"])
+for kv in os.environ.get("TCSDN_TOOL_OPTS", "").split(","):   # e.g. TCSDN_TOOL_OPTS=8=0,7=16 -> tcsdn_set_option(key, value)
+    if kv:
+        est.set_option(int(kv.split("=")[0]), int(kv.split("=")[1]))
 X = bench.synth_rows(rows, w["d"], seed=1000, device=torch.device("cuda", 0))
 out = torch.empty(rows, dtype=torch.int32, device="cuda")
 for _ in range(reps):

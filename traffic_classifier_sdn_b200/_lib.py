@@ -14,6 +14,7 @@ F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 OK, EINVAL, ECUDA, ENOMEM, ENONFINITE = 0, -1, -2, -3, -4
 OPT_ENGINE, OPT_CHUNK_ROWS, OPT_CHECK_FINITE = 1, 2, 3
+OPT_SCORER_SHAPE, OPT_FOREST_SHAPE, OPT_FOREST_SORT, OPT_KNN_FLUSH_TILES = 4, 5, 6, 7
 FLOW_STATE = 19
 COMM_ID_BYTES = 128
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "tcsdn_comm_unique_id": (C.c_int, [_vp]),
     "tcsdn_comm_init": (C.c_int, [C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]),
     "tcsdn_allgather_labels": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "tcsdn_allgather_labels_u8": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp]),
     "tcsdn_comm_destroy": (None, [_vp]),
 }
 

@@ -28,12 +28,14 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link libtcsdn.so.  Returns the library path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every .cu for sm_100a and link libtcsdn.so.  Returns the library path.
+    `extra_flags` / `out`: experiment builds (e.g. -DTCSDN_EXP_NO_EX2) into another file, tools/ only."""
+    lib_out = out or LIB
+    if not force and not out and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not out else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)
@@ -41,7 +43,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
     objs, log = [], []
     for src, obj, p in procs:
@@ -53,11 +55,11 @@ def build(force=False, verbose=False):
         objs.append(obj)
     with open(os.path.join(objdir, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++", "-shared", "-o", LIB] + objs + ["-lcuda", "-ldl"]
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++", "-shared", "-o", lib_out] + objs + ["-lcuda", "-ldl"]
     subprocess.check_call(cmd, env=env)
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

@@ -26,18 +26,18 @@ static int model_base(tcsdn_model **out, int kind, int d, int n_classes, int sco
         set_error("no CUDA device available (%s); libtcsdn has no CPU path", cudaGetErrorString(e));
         return TCSDN_ECUDA;
     }
-    tcsdn_model *m = new (std::nothrow) tcsdn_model();
-    if (!m) { set_error("out of host memory"); return TCSDN_ENOMEM; }
-    m->kind = kind; m->d = d; m->n_classes = n_classes; m->score_cols = score_cols;
-    TCSDN_CUDA(cudaGetDevice(&m->dev));
+    int dev = 0;
+    TCSDN_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, m->dev);
-    if (e != cudaSuccess) { delete m; set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
     if (prop.major < 10) {
-        delete m;
-        set_error("device %d is sm_%d%d; libtcsdn is built for sm_100a (B200) only", m->dev, prop.major, prop.minor);
+        set_error("device %d is sm_%d%d; libtcsdn is built for sm_100a (B200) only", dev, prop.major, prop.minor);
         return TCSDN_ECUDA;
     }
+    tcsdn_model *m = new (std::nothrow) tcsdn_model();
+    if (!m) { set_error("out of host memory"); return TCSDN_ENOMEM; }
+    m->kind = kind; m->d = d; m->n_classes = n_classes; m->score_cols = score_cols; m->dev = dev;
     m->sm_count = prop.multiProcessorCount;
     e = cudaMalloc((void **)&m->d_flag, sizeof(int32_t));
     if (e != cudaSuccess) { delete m; set_error("cudaMalloc: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
@@ -61,6 +61,7 @@ static void free_workspace(Workspace *w) {
         if (w->done[i]) cudaEventDestroy(w->done[i]);
     }
     if (w->h_flag) cudaFreeHost(w->h_flag);
+    cudaFree(w->d_flag);
     delete w;
 }
 
@@ -95,6 +96,7 @@ static int acquire_workspace(tcsdn_model *m, Workspace **out) {
         TCSDN_CUDA(cudaEventCreateWithFlags(&w->done[i], cudaEventDisableTiming));
     }
     TCSDN_CUDA(cudaMallocHost((void **)&w->h_flag, sizeof(int32_t)));
+    TCSDN_CUDA(cudaMalloc((void **)&w->d_flag, sizeof(int32_t)));
     w->in_use = true;
     m->pool.push_back(w);
     *out = w;
@@ -106,21 +108,27 @@ static void release_workspace(tcsdn_model *m, Workspace *w) {
     w->in_use = false;
 }
 
+// `flag`: where the kernels record non-finite rows -- the handle's sticky flag for device-pointer predicts (read by
+// tcsdn_sync_check), the workspace's own for host-pointer predicts (so that concurrent calls cannot see or clear
+// each other's)
 static int run_device(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                      cudaStream_t st) {
+                      int32_t *flag, cudaStream_t st) {
+    if (!m->opt_check_finite) flag = nullptr;
     switch (m->kind) {
         case TCSDN_KIND_LINEAR:
         case TCSDN_KIND_GNB:
-        case TCSDN_KIND_KMEANS: return launch_scorer(m, x, n, dtype, labels, scores, st);
-        case TCSDN_KIND_FOREST: return launch_forest(m, x, n, dtype, labels, scores, st);
+        case TCSDN_KIND_KMEANS: return launch_scorer(m, x, n, dtype, labels, scores, flag, st);
+        case TCSDN_KIND_FOREST: return launch_forest(m, x, n, dtype, labels, scores, flag, st);
         case TCSDN_KIND_KNN:
-            if (m->opt_engine != 1 && engine_usable(m, n)) return launch_engine(m, x, n, dtype, labels, scores, st);
+            if (m->opt_engine != 1 && engine_usable(m, n, scores != nullptr)) return launch_engine(m, x, n, dtype, labels, scores, flag, st);
             if (m->opt_engine >= 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
-            return launch_knn_exact(m, x, n, dtype, labels, scores, st);
+            return launch_knn_exact(m, x, n, dtype, labels, scores, flag, st);
         case TCSDN_KIND_SVC:
-            if (m->opt_engine != 1 && engine_usable(m, n)) return launch_engine(m, x, n, dtype, labels, scores, st);
-            if (m->opt_engine >= 2) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
-            return launch_svc_exact(m, x, n, dtype, labels, scores, st);
+            // decision values are always the fp64 kernel's (the engine certifies LABELS; its fp32 sums cannot meet a
+            // 1e-5 absolute bound on decision values, see dist_engine.cu)
+            if (m->opt_engine != 1 && engine_usable(m, n, scores != nullptr)) return launch_engine(m, x, n, dtype, labels, scores, flag, st);
+            if (m->opt_engine >= 2 && !scores) { set_error("tensor-core engine forced but not usable for this model/batch"); return TCSDN_EINVAL; }
+            return launch_svc_exact(m, x, n, dtype, labels, scores, flag, st);
     }
     set_error("corrupt model handle");
     return TCSDN_EINVAL;
@@ -358,12 +366,22 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
     if (!m) { set_error("model is NULL"); return TCSDN_EINVAL; }
     switch (key) {
         case TCSDN_OPT_ENGINE:
-            if (value < 0 || value > 3) { set_error("engine option must be 0..3"); return TCSDN_EINVAL; }
+            if (value < 0 || value > 4) { set_error("engine option must be 0..4"); return TCSDN_EINVAL; }
             m->opt_engine = value; return TCSDN_OK;
         case TCSDN_OPT_CHUNK_ROWS:
             if (value < 0) { set_error("chunk rows must be >= 0"); return TCSDN_EINVAL; }
             m->opt_chunk_rows = value; return TCSDN_OK;
         case TCSDN_OPT_CHECK_FINITE: m->opt_check_finite = value ? 1 : 0; return TCSDN_OK;
+        case TCSDN_OPT_SCORER_SHAPE:
+            if (value < 0 || value > 2) { set_error("scorer shape must be 0..2"); return TCSDN_EINVAL; }
+            m->opt_scorer_shape = value; return TCSDN_OK;
+        case TCSDN_OPT_FOREST_SHAPE:
+            if (value < 0 || value > 2) { set_error("forest shape must be 0..2"); return TCSDN_EINVAL; }
+            m->opt_forest_shape = value; return TCSDN_OK;
+        case TCSDN_OPT_FOREST_SORT: m->opt_forest_sort = value ? 1 : 0; return TCSDN_OK;
+        case TCSDN_OPT_KNN_FLUSH_TILES:
+            if (value < 0 || value > 31) { set_error("knn flush tiles must be 0..31"); return TCSDN_EINVAL; }
+            m->opt_knn_flush = value; return TCSDN_OK;
     }
     set_error("unknown option key %d", key);
     return TCSDN_EINVAL;
@@ -371,8 +389,8 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
 
 int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out) {
     if (!m || !out) { set_error("NULL argument"); return TCSDN_EINVAL; }
-    for (int i = 0; i < 8; ++i) out[i] = m->stats[i];
-    if (m->engine) engine_read_stats(m, &out[3], &out[5]);   // cumulative since create(); synchronises the device
+    for (int i = 0; i < 8; ++i) out[i] = m->stats[i].load(std::memory_order_relaxed);
+    if (m->engine) engine_read_stats(m, out);   // cumulative since create(); synchronises the device
     if (m->d_refined) {   // cumulative since create(); synchronises the device
         unsigned long long v = 0;
         if (cudaMemcpy(&v, m->d_refined, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) out[6] = (int64_t)v;
@@ -392,15 +410,20 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
     if (x_loc != TCSDN_HOST && x_loc != TCSDN_DEVICE) { set_error("x_loc must be TCSDN_HOST or TCSDN_DEVICE"); return TCSDN_EINVAL; }
     if (n == 0) return TCSDN_OK;
     if (!x || !labels_out) { set_error("x / labels_out is NULL"); return TCSDN_EINVAL; }
+    // run on the handle's device and give the caller's current device back on every exit path
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
     int cur = -1;
     TCSDN_CUDA(cudaGetDevice(&cur));
-    if (cur != m->dev) TCSDN_CUDA(cudaSetDevice(m->dev));
-    for (int i = 0; i < 8; ++i) m->stats[i] = 0;
+    if (cur != m->dev) { TCSDN_CUDA(cudaSetDevice(m->dev)); guard.prev = cur; }
+    for (int i = 0; i < 8; ++i) m->stats[i].store(0, std::memory_order_relaxed);
 
     if (x_loc == TCSDN_DEVICE) {
         // the non-finite flag is sticky on this path: kernels only OR into it, tcsdn_sync_check reads and clears it
         // (no memset node per predict: a 1M-row predict lasts microseconds)
-        return run_device(m, x, n, x_dtype, labels_out, scores_out, static_cast<cudaStream_t>(cuda_stream));
+        return run_device(m, x, n, x_dtype, labels_out, scores_out, m->d_flag, static_cast<cudaStream_t>(cuda_stream));
     }
 
     // host pointers: chunks alternate between two internal streams, so the H2D copy of chunk c+1 runs under the
@@ -444,7 +467,7 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
     };
     do {
         if (m->opt_check_finite) {
-            cudaError_t e = cudaMemsetAsync(m->d_flag, 0, sizeof(int32_t), w->stream[0]);
+            cudaError_t e = cudaMemsetAsync(w->d_flag, 0, sizeof(int32_t), w->stream[0]);
             if (e == cudaSuccess) e = cudaEventRecord(w->done[1], w->stream[0]);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(w->stream[1], w->done[1], 0);
             if (e != cudaSuccess) { set_error("flag reset failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; break; }
@@ -466,7 +489,7 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
                                             (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; break; }
             rc = run_device(m, w->x[slot].p, rows, x_dtype, static_cast<int32_t *>(w->labels[slot].p),
-                            sc_cols ? static_cast<double *>(w->scores[slot].p) : nullptr, st);
+                            sc_cols ? static_cast<double *>(w->scores[slot].p) : nullptr, w->d_flag, st);
             if (rc != TCSDN_OK) break;
             e = cudaMemcpyAsync(direct_out ? (void *)(labels_out + done) : w->h_labels[slot], w->labels[slot].p,
                                 (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
@@ -488,10 +511,9 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
             if (e != cudaSuccess && rc == TCSDN_OK) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; }
         }
         if (rc == TCSDN_OK && m->opt_check_finite) {
-            cudaError_t e = cudaMemcpy(w->h_flag, m->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaMemcpy(w->h_flag, w->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { set_error("flag read failed: %s", cudaGetErrorString(e)); rc = TCSDN_ECUDA; }
             else if (*w->h_flag) {
-                cudaMemset(m->d_flag, 0, sizeof(int32_t));
                 set_error("Input X contains NaN or infinity");
                 rc = TCSDN_ENONFINITE;
             }

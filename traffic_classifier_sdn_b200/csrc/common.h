@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -64,6 +65,7 @@ struct Workspace {  // per-call scratch for the host-pointer pipeline
     cudaStream_t stream[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     int32_t *h_flag = nullptr;  // pinned
+    int32_t *d_flag = nullptr;  // this call's non-finite flag (host-pointer predicts; device-pointer predicts use the handle's)
     bool in_use = false;
 };
 
@@ -80,7 +82,12 @@ struct tcsdn_model {
     int64_t opt_engine = 0;
     int64_t opt_chunk_rows = 0;
     int64_t opt_check_finite = 1;
-    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t opt_scorer_shape = 0;    // 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2
+    int64_t opt_forest_shape = 0;    // 0 auto (1024 x 1), 1 = 512 x 2, 2 = 256 x 4
+    int64_t opt_forest_sort = 1;     // coherence sort on/off
+    int64_t opt_knn_flush = 0;       // tiles between two evaluation rounds of the knn engine; 0 = default
+    // counters of the last predict; atomics because several host threads may predict on one handle (they then add up)
+    std::atomic<int64_t> stats[8] = {};
 
     // ---- streaming scorers
     tcsdn::ScorerParams sp;          // valid when n_classes <= kMaxClassesFast && d <= 16
@@ -122,14 +129,15 @@ struct tcsdn_model {
 namespace tcsdn {
 
 // kernels' host launchers (each enqueues on `st`, returns TCSDN_*).  x is a DEVICE pointer.
+// `flag` (nullable): device int32 the kernels OR 1 into when a row holds NaN/inf.
 int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  cudaStream_t st);
+                  int32_t *flag, cudaStream_t st);
 int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  cudaStream_t st);
+                  int32_t *flag, cudaStream_t st);
 int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                     cudaStream_t st);
+                     int32_t *flag, cudaStream_t st);
 int launch_svc_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                     cudaStream_t st);
+                     int32_t *flag, cudaStream_t st);
 int launch_ovr_from_ovo(const double *dec, int64_t n, int C, double *out, cudaStream_t st);
 int launch_flow_update(double *state, const double *packets, const double *bytes, const double *curr_time,
                        const uint8_t *dir, int64_t n, void *features_out, int feat_dtype, cudaStream_t st);
@@ -140,10 +148,14 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
 // tensor-core distance engine (dist_engine.cu)
 int engine_create(tcsdn_model *m);   // builds packed operands for knn / svc handles
 void engine_destroy(tcsdn_model *m);
-bool engine_usable(const tcsdn_model *m, int64_t n);
-void engine_read_stats(const tcsdn_model *m, int64_t *exact_evals, int64_t *maxratio_q40);
+bool engine_usable(const tcsdn_model *m, int64_t n, bool want_scores);
+void engine_read_stats(const tcsdn_model *m, int64_t *out8);
+// svc.cu: re-evaluate, in fp64, exactly the rows whose label is negative (-1 - label, left by the engine's certificate);
+// `counter` (device) receives the number of such rows
+int launch_svc_marked(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, unsigned long long *counter,
+                      cudaStream_t st);
 int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  cudaStream_t st);
+                  int32_t *flag, cudaStream_t st);
 
 template <typename T>
 int upload(T **dst, const T *src, size_t count) {

@@ -15,27 +15,52 @@
 // acc <= (worst kept distance - ||x||^2) + kappa (||x||^2 + ||t||^2), kappa = 2^-18; every row the sequential heap
 // would accept passes, every row that passes goes through the same heap_push in index order -> neighbours
 // identical to knn.cu / sklearn.  (The kappa ||t||^2 part is folded into the packed norm: B carries (1-kappa)||t||^2.)
-// SVC uses acc directly: e = -gamma log2(e) (acc + ||x - c_j||^2), K = ex2(e), C-1 fp32 FMAs per pair into the running
-// sums of the support vector's class, tile sums promoted to fp64 (tolerance: tests/test_engine_gpu.py).  To keep the
-// fp32 accumulation error small where K is not negligible, support vectors are re-ordered inside their class into
-// spatially compact tiles and every tile is expanded around ITS OWN centre c_j: B holds u = s - c_j, three extra K
-// slots hold the scalar 2 (c_j - c0).u, so the (globally centred) A operand effectively becomes x - c_j, and the
-// epilogue adds ||x - c_j||^2 computed directly in fp32.  The error is then 2^-21 (|x - c_j| r_j) instead of
-// 2^-21 (||x||^2 + ||s||^2).
+// SVC uses acc directly, for LABELS only: e = -gamma log2(e) (acc + ||x' - c'_j||^2), K = ex2(e), C-1 fp32 FMAs per pair into
+// the running sums of the support vector's class, tile sums promoted to fp64.  To keep the fp32 accumulation error small
+// where K is not negligible, support vectors are re-ordered inside their class into spatially compact tiles and every tile
+// is expanded around ITS OWN centre c'_j (an fp32 vector, relative to the global centre c0): B holds u = (s - c0) - c'_j,
+// three extra K slots hold the scalar 2 c'_j.u, so the (globally centred) A operand x' = fl32(x - c0) effectively becomes
+// x' - c'_j, and the epilogue adds ||x' - c'_j||^2 computed directly in fp32.
+//
+// The certificate (what makes the engine's labels the fp64 definition's labels).  fp32 distances cannot give decision
+// values to 1e-5 -- gamma * delta(d) * sum|coef K| is 1e-4..1e-3 on the reference's own model -- so decision VALUES always
+// come from the fp64 kernel (svc.cu) and the engine only has to get the VOTE right.  Per row and per pair p it carries a
+// bound E_p on |dec~_p - dec_p|:
+//   * libsvm's dual coefficients have one sign per (class, opponent) -- alpha_s y_s with y = +1 for the lower class of the
+//     pair (sk:svm/src/libsvm/svm.cpp:2093-2118) -- so inside a (single-class) tile every term of tsum_m = sum_s coef_ms K_s
+//     has the same sign and |tsum_m| IS sum_s |coef_ms| K_s: no extra accumulation (create() checks the sign pattern
+//     and keeps a model that violates it on the fp64 kernel);
+//   * every K~_s of tile j is off by a relative eta_j at most:  eta_j = gamma delta_d + eta_const,
+//       delta_d <= eps_mma M_j + 2^-20 xn + 2^-24 (xn + qn) + 2^-23 r_j sqrt(qn)
+//       M_j = r_j (2 sqrt(qn) + r_j + 2 |c'_j|) >= the sum of the absolute values of the MMA's products
+//     (qn = ||x'||^2, xn = ||x' - c'_j||^2, r_j = max ||u||; the 2^-24 / 2^-23 terms are the roundings of x' and u:
+//     the engine measures the distance from a point within 2^-24 |x - c0| of x), eps_mma = kSvcEpsMma is 4x the
+//     largest |acc - exact| / M_j the all-pairs audit observes (tests/test_engine_gpu.py), eta_const = 1.65e-6 covers
+//     ex2.approx (2^-22), the fp32 coefficient (2^-24), the fma that forms e where |e| <= 4 (ln2 2^-24 |e|) and the fp32
+//     sums: four chains of 16 terms per tile (15 u), their combination (2 u) and a compensated (Kahan) class sum (2 u);
+//   * E_p = 1.25 sum_j eta_j |tsum_j,m(p)| + Eabs_p,  Eabs_p = 1.04e-8 sum_s |coef_s| + 1e-9: where |e| > 4 the rounding of
+//     e costs coef K at most 1.04e-8 |coef| in absolute terms (|e| 2^-|e| <= 1/4); the rest covers second order, the float
+//     accumulation of E itself and ex2's flush to zero.
+// A pair is UNCERTAIN when |dec~_p| <= E_p.  The row's label is certified when no assignment of the uncertain pairs can
+// change libsvm's first-maximum vote (svm.cpp:2893-2896); otherwise the kernel stores -1 - label and the fp64 kernel
+// re-evaluates exactly those rows in the same call (svc.cu, launch_svc_marked) -- the GaussianNB pattern of scorers.cu.
 //
 // Data layout.  create() packs the reference rows once into tile images of 64 rows x K=80 bf16 in the UMMA
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
-// followed (SVC) by the tile's dual coefficients [C-1][64] fp32 and its centre.  A tile image is contiguous in HBM, so
+// followed (SVC) by the tile's dual coefficients [C-1][64] fp32, its centre c'_j and the two constants of eta_j.  A tile image is contiguous in HBM, so
 // one cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
 // boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows (even row
 // stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.
 //
-// Kernel (persistent, 1 CTA / SM, 576 threads).  A CTA owns 512 query rows at a time:
-//   warps 0-15  each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
+// Kernel (persistent, 1 CTA / SM).  A CTA owns 512 query rows at a time:
+//   KNN: warps 0-15, each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
 //               memory, same canonical layout), later reads its accumulator row from TMEM (tcgen05.ld 32x32b)
-//               and runs the KNN filter / SVC exp-and-accumulate epilogue on 64 columns per reference tile;
-//   warp 16     one lane streams reference tile images through a 4-stage ring (bulk copy + mbarrier tx count);
-//   warp 17     runs warp-uniformly; one ELECTED lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per
+//               and runs the filter epilogue on 64 columns per reference tile;
+//   SVC: warps 0-7, each thread owns TWO query rows (the same TMEM lane of two query tiles), so that one broadcast
+//               LDS.128 of dual coefficients feeds two rows: the coefficient loads were the kernel's bound (shared-memory
+//               return bandwidth, profiles/r01e), not the ex2 unit;
+//   next warp   one lane streams reference tile images through a 4-stage ring (bulk copy + mbarrier tx count);
+//   last warp   runs warp-uniformly; one ELECTED lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per
 //               reference tile into a double-buffered TMEM accumulator (4 tiles x 2 buffers x 64 columns = all 512
 //               columns) and commits to the ring's "empty" barrier and the accumulator's "full" barrier.
 // Each reference tile (10 KB) is reused by 512 query rows: 16 B/clk/SM of L2 traffic against 640 clk of MMA.
@@ -54,13 +79,17 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
 
 namespace tcsdn {
 
-constexpr int kEThreads = 576;       // 16 epilogue warps + producer warp + MMA warp
+constexpr int kEKnnWarps = 16;       // KNN epilogue warps (one query row per thread)
+constexpr int kESvcWarps = 8;        // SVC epilogue warps (two query rows per thread)
+constexpr int kEKnnThreads = (kEKnnWarps + 2) * 32;   // + producer warp + MMA warp
+constexpr int kESvcThreads = (kESvcWarps + 2) * 32;
 constexpr int kERows = 512;          // query rows per CTA pass (4 MMA tiles of 128)
 constexpr int kEN = 64;              // reference rows per tile (MMA N)
 constexpr int kEK = 80;              // packed K
@@ -71,7 +100,9 @@ constexpr int kETileB = kEN * kEK * 2;      // 10240 bytes of bf16 per reference
 constexpr int kEATile = 128 * kEK * 2;      // 20480 bytes per query tile
 constexpr int kESBO = (kEK / 8) * 128;      // 1280
 constexpr int kEMaxK = 32;                  // neighbours kept per query in the engine
-constexpr int kEMaxNC1 = 7;                 // SVC: n_classes - 1
+constexpr int kEMaxNC1 = 5;                 // SVC: n_classes - 1 (the per-pair sums and bounds of 512 rows live in shared memory)
+constexpr float kSvcEpsMma = 1.0f / 524288.0f;   // 2^-19: bound on |acc - exact| / M_j; 4x the all-pairs audit's maximum
+constexpr float kSvcEtaConst = 1.65e-6f;         // relative part of the K error that does not depend on distances (file header)
 constexpr float kKappa = 1.0f / 262144.0f;  // 2^-18: filter slack per unit of (||x||^2 + ||t||^2); 8x the largest error the
                                             // all-pairs audit observes (2^-21.0 .. 2^-20.4, tests/test_engine_gpu.py)
 constexpr int kEListCap = 24;               // per-thread candidate list, 16-bit entries (tile offset, group of 8 columns, mask)
@@ -85,11 +116,13 @@ struct EngineState {
     int32_t *d_tile_rows = nullptr;     // per tile: number of real rows
     double *d_center = nullptr;         // [d]
     double *d_refpad = nullptr;         // KNN: original fp64 reference rows, row stride padded to an even count (16 B loads)
-    float *d_maxratio = nullptr;        // audit: max observed |acc - exact| / (||x||^2 + ||t||^2)
-    unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN)
+    float *d_maxratio = nullptr;        // audit: max observed |acc - exact| / (||x||^2 + ||t||^2)  (SVC: / M_j)
+    unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN) / rows handed to the fp64 kernel (SVC)
     int n_tiles = 0;
     int tile_bytes = 0;
     int nc1 = 0;
+    bool certifiable = true;            // SVC: the dual coefficients have libsvm's sign pattern (see the file header)
+    float eabs[(kEMaxNC1 + 1) * kEMaxNC1 / 2] = {};   // SVC: per pair, the absolute part of the bound
 };
 
 struct EngineArgs {
@@ -106,7 +139,11 @@ struct EngineArgs {
     int32_t *flag;
     int64_t n;
     int n_tiles, tile_bytes, d, dpad, k, C, nc1, flush_tiles, n_ref;
+    int svc_mode;            // SVC: 0 = labels, uncertified rows stored as -1 - label; 3 = raw labels + decision values in
+                             // scores (audit, also records the MMA error ratio); 4 = raw labels + the bounds E_p in scores
     float g2;                // SVC: -gamma * log2(e)
+    float svc_c1, svc_c2;    // SVC: gamma (2^-20 + 2^-24) and gamma 2^-24, the row-dependent parts of eta_j
+    float svc_eabs[(kEMaxNC1 + 1) * kEMaxNC1 / 2];   // SVC: per pair, the absolute part of E_p (file header)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -283,19 +320,90 @@ __device__ __forceinline__ float knn_thr_base(double hv0, double qn) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <typename T, bool SVC, int NC1>
-__global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X,
-                                                              int32_t *__restrict__ labels, double *__restrict__ scores,
-                                                              unsigned long long *__restrict__ counters) {
+// 8-column TMEM load (issue only) and the matching wait for two of them
+__device__ __forceinline__ void e_tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+#if defined(TCSDN_EXP_NO_LDTM)   // experiment build: no TMEM loads (registers get the address instead)
+    for (int i = 0; i < 8; ++i) r[i] = 0xBF000000u + (taddr & 0xFFFFu) + i;
+    return;
+#endif
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void e_tmem_ld8_wait2(uint32_t (&r)[8], uint32_t (&q)[8]) {
+#if defined(TCSDN_EXP_NO_LDTM)
+    return;
+#endif
+    // no "memory" clobber: the register operands carry the dependency, and the compiler stays free to move coefficient
+    // loads and FMAs across the wait
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]));
+}
+
+// two 16-column TMEM loads complete (both register sets are named as in/out operands: no use may move above the wait)
+__device__ __forceinline__ void e_tmem_ld16_wait2(uint32_t (&r)[16], uint32_t (&q)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]),
+                   "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]));
+    // no "memory" clobber: the register operands carry the dependency, and the compiler stays free to move the next
+    // chunk's coefficient loads and FMAs across the wait
+}
+
+// Load one query row, centre it on c0, round to fp32 (x'), split -2 x' into three bf16 pieces and write the row of the A
+// operand (query tile qt, TMEM lane rt).  Returns ||x'||^2 (fp64); xp receives x' (zeros for a dead row).
+template <typename T, bool SVC>
+__device__ __forceinline__ double e_pack_row(const EngineArgs &A, const T *__restrict__ X, int64_t row, bool live,
+                                             unsigned char *sA, int qt, int rt, float &nf, float (&xp)[kEMaxD]) {
+    double qn = 0.0;
+    __align__(16) __nv_bfloat16 pk[kEK];
+#pragma unroll
+    for (int i = 0; i < kEK; ++i) pk[i] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < kEMaxD; ++j) {
+        xp[j] = 0.f;
+        if (j < A.d && live) {
+            const T v = X[row * A.d + j];
+            nf += static_cast<float>(v * static_cast<T>(0));
+            const float c32 = static_cast<float>(static_cast<double>(v) - A.center[j]);
+            xp[j] = c32;
+            qn += (double)c32 * (double)c32;
+            __nv_bfloat16 h, m, l;
+            split3(-2.0f * c32, h, m, l);
+            pk[kslot(0, j, A.d)] = h; pk[kslot(1, j, A.d)] = h; pk[kslot(2, j, A.d)] = m;
+            pk[kslot(3, j, A.d)] = m; pk[kslot(4, j, A.d)] = h; pk[kslot(5, j, A.d)] = l;
+        }
+    }
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+    pk[6 * A.d + 0] = one; pk[6 * A.d + 1] = one; pk[6 * A.d + 2] = one;
+    if (SVC) { pk[6 * A.d + 3] = one; pk[6 * A.d + 4] = one; pk[6 * A.d + 5] = one; }   // the 2 c'_j.u slots
+    unsigned char *dst = sA + qt * kEATile + (rt >> 3) * kESBO + (rt & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < kEK / 8; ++c)
+        *reinterpret_cast<uint4 *>(dst + c * 128) = *reinterpret_cast<const uint4 *>(&pk[c * 8]);
+    return qn;
+}
+
+// AUDIT (SVC; KNN keeps its audit flag in NC1): a separate instantiation, because the audit indexes the accumulator registers
+// and x' dynamically, which would put them in local memory in the production kernel too
+template <typename T, bool SVC, int NC1, bool AUDIT = false>
+__global__ void __launch_bounds__(SVC ? kESvcThreads : kEKnnThreads, 1)
+engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int32_t *__restrict__ labels,
+              double *__restrict__ scores, unsigned long long *__restrict__ counters) {
+    constexpr int kEpi = SVC ? kESvcWarps : kEKnnWarps;   // epilogue warps; then the producer warp, then the MMA warp
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem;                                          // 4 x 20480
     unsigned char *sB = smem + 4 * kEATile;                            // kEStages x tile_bytes
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kEStages * A.tile_bytes);
     uint64_t *fullB = bars, *emptyB = bars + kEStages, *accFull = bars + 2 * kEStages, *accEmpty = accFull + 2;
     uint64_t *aFull = accEmpty + 2;
-    uint64_t *coefFree = aFull + 1;      // the 16 epilogue warps are done with a stage's side data (SVC coefficients, KNN fp64 rows)
+    uint64_t *coefFree = aFull + 1;      // the epilogue warps are done with a stage's side data (SVC coefficients)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(coefFree + kEStages);
-    unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + 256;   // KNN: [512 threads][kEListCap] column indices
+    // after the barriers -- KNN: [512 threads][kEListCap] candidate lists, then the heaps; SVC: [P][512] fp64 pair sums,
+    // then [P][512] fp32 error bounds
+    unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_super = (A.n + kERows - 1) / kERows;
@@ -303,17 +411,17 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
     if (tid == 0) {
         for (int s = 0; s < kEStages; ++s) {
             e_mbar_init(&fullB[s], 1);
-            e_mbar_init(&emptyB[s], 1);      // tcgen05.commit: the MMAs have read the stage
-            e_mbar_init(&coefFree[s], 16);   // every epilogue warp has read the stage's side data
+            e_mbar_init(&emptyB[s], 1);        // tcgen05.commit: the MMAs have read the stage
+            e_mbar_init(&coefFree[s], kEpi);   // every epilogue warp has read the stage's side data
         }
         for (int b = 0; b < 2; ++b) {
             e_mbar_init(&accFull[b], 1);
-            e_mbar_init(&accEmpty[b], 16);
+            e_mbar_init(&accEmpty[b], kEpi);
         }
-        e_mbar_init(aFull, 16);
+        e_mbar_init(aFull, kEpi);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 17) {
+    if (warp == kEpi + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(e_smem(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -322,7 +430,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 16) {
+    if (warp == kEpi) {
         // ------------------------------------------------------------------ reference tile producer
         if (lane == 0) {
             uint32_t g = 0;
@@ -336,7 +444,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == kEpi + 1) {
         // ------------------------------------------------------------------ MMA issuer
         // The whole warp runs this loop (warp-uniform control flow, so descriptors live in uniform registers) and ONE
         // elected lane issues.  Issuing from `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma in an
@@ -364,7 +472,13 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     for (int t = 0; t < 4; ++t) {
                         const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
 #pragma unroll
+#if defined(TCSDN_EXP_NO_MMA)     // experiment build: no MMA at all (commits only)
+                        for (int k = 0; k < 0; ++k)
+#elif defined(TCSDN_EXP_ONE_MMA)  // experiment build: one K step instead of five (a fifth of the operand reads)
+                        for (int k = 0; k < 1; ++k)
+#else
                         for (int k = 0; k < kEKSteps; ++k)
+#endif
                             e_mma(dcol, desc_hi | (uint64_t)(a_lo + (uint32_t)(t * (kEATile >> 4) + k * 16)),
                                   desc_hi | (uint64_t)(b_lo + (uint32_t)(k * 16)), idesc, k > 0);
                     }
@@ -374,8 +488,8 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                 __syncwarp();
             }
         }
-    } else {
-        // ------------------------------------------------------------------ 512 query-row owners (pack A, epilogue)
+    } else if constexpr (!SVC) {
+        // ------------------------------------------------------------------ KNN: 512 query-row owners (pack A, filter epilogue)
         const int qt = warp >> 2;                           // query tile 0..3
         const int rt = (warp & 3) * 32 + lane;              // row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -384,41 +498,13 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
         for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
             const int64_t row = st * kERows + qt * 128 + rt;
             const bool live = row < A.n;
-            // ---- load, centre, split and pack this row into the A operand
-            T qx[kEMaxD];
-            double qn = 0.0;
-            {
-                __align__(16) __nv_bfloat16 pk[kEK];
-#pragma unroll
-                for (int i = 0; i < kEK; ++i) pk[i] = __float2bfloat16_rn(0.f);
-#pragma unroll
-                for (int j = 0; j < kEMaxD; ++j) {
-                    qx[j] = static_cast<T>(0);
-                    if (j < A.d && live) {
-                        const T v = X[row * A.d + j];
-                        nf += static_cast<float>(v * static_cast<T>(0));
-                        qx[j] = v;
-                        const float c32 = static_cast<float>(static_cast<double>(v) - A.center[j]);
-                        qn += (double)c32 * (double)c32;
-                        __nv_bfloat16 h, m, l;
-                        split3(-2.0f * c32, h, m, l);
-                        pk[kslot(0, j, A.d)] = h; pk[kslot(1, j, A.d)] = h; pk[kslot(2, j, A.d)] = m;
-                        pk[kslot(3, j, A.d)] = m; pk[kslot(4, j, A.d)] = h; pk[kslot(5, j, A.d)] = l;
-                    }
-                }
-                const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
-                pk[6 * A.d + 0] = one; pk[6 * A.d + 1] = one; pk[6 * A.d + 2] = one;
-                if (SVC) { pk[6 * A.d + 3] = one; pk[6 * A.d + 4] = one; pk[6 * A.d + 5] = one; }   // 2 (c_j - c0).u slots
-                unsigned char *dst = sA + qt * kEATile + (rt >> 3) * kESBO + (rt & 7) * 16;
-#pragma unroll
-                for (int c = 0; c < kEK / 8; ++c)
-                    *reinterpret_cast<uint4 *>(dst + c * 128) = *reinterpret_cast<const uint4 *>(&pk[c * 8]);
-            }
+            float xp_unused[kEMaxD];
+            const double qn = e_pack_row<T, false>(A, X, row, live, sA, qt, rt, nf, xp_unused);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
             __syncwarp();
             if (lane == 0) e_mbar_arrive(aFull);
 
-            if constexpr (!SVC) {
+            {
                 // ================================================================ KNN: filter, deferred exact heap
                 // acc = (1 - kappa) ||t||^2 - 2 x.t, so a row passes iff acc <= thr = (worst kept distance - ||x||^2)
                 // + kappa ||x||^2.  Passing columns are appended to a per-thread list (tile offset << 6 | column) and the
@@ -558,7 +644,7 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                                         const double *t = A.ref + (size_t)tr * A.d;
                                         double dist = 0.0, tn = 0.0;
                                         for (int jj = 0; jj < A.d; ++jj) {
-                                            const double df = static_cast<double>(qx[jj]) - t[jj], u = t[jj] - A.center[jj];
+                                            const double df = static_cast<double>(X[row * A.d + jj]) - t[jj], u = t[jj] - A.center[jj];
                                             dist += df * df; tn += u * u;
                                         }
                                         const float ratio = (float)(fabs((double)v[gq * 8 + c] - ((dist - qn) - (double)kKappa * tn)) / (qn + tn + 1e-30));
@@ -581,130 +667,326 @@ __global__ void __launch_bounds__(kEThreads, 1) engine_kernel(const __grid_const
                     labels[row] = arg;
                     if (counters) atomicAdd(counters, n_exact);
                 }
-            } else {
-                // ================================================================ SVC: exp + one-vs-one sums
-                // Every support-vector tile carries its own centre c_j (tiles are spatially compact, see create()):
-                //   acc = ||u||^2 - 2 (x - c_j).u,  u = s - c_j      (B holds u and the scalar 2 (c_j - c0).u per row)
-                //   d   = ||x - c_j||^2 + acc ,  ||x - c_j||^2 summed directly in fp32 (no cancellation)
-                // so the fp32 accumulation error scales with |x - c_j| r_j instead of ||x||^2 + ||s||^2.
-                const float g2 = A.g2;
-                float x32[kEMaxD];
+            }
+        }
+        if (A.flag && nf != nf) atomicOr(A.flag, 1);
+    } else {
+        // ------------------------------------------------------------------ SVC: 8 warps x 2 query rows per thread
+        // Every support-vector tile carries its own centre c'_j (tiles are spatially compact, see create()):
+        //   acc = ||u||^2 - 2 (x' - c'_j).u,  u = (s - c0) - c'_j   (B holds u and the scalar 2 c'_j.u per row)
+        //   d   = ||x' - c'_j||^2 + acc ,  ||x' - c'_j||^2 summed directly in fp32 (no cancellation)
+        // A warp covers one TMEM lane quadrant of TWO query tiles, so one broadcast LDS.128 of coefficients serves both rows.
+        constexpr int C = NC1 + 1, P = C * NC1 / 2;
+        const int quad = warp & 3, hsel = warp >> 2;
+        const int rt = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        double *decS = reinterpret_cast<double *>(cand);            // [P][512]: sum over finished classes of coef K
+        float *errS = reinterpret_cast<float *>(decS + P * kERows); // [P][512]: the matching error bound
+        const int slot0 = (2 * hsel) * 128 + rt;                    // this thread's rows sit at slot0 and slot0 + 128
+        const float g2 = A.g2;
+        uint32_t g = 0;
+        float nf = 0.f;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+            int64_t row[2];
+            bool live[2];
+            float xp[2][kEMaxD], sq[2], c2row[2];
 #pragma unroll
-                for (int j = 0; j < kEMaxD; ++j) x32[j] = (float)qx[j];
-                float2 tsum[NC1];                                     // (even, odd) column partial sums: one FFMA2 per column pair
-                double csum[NC1];
-                double S[(NC1 + 1) * NC1];                            // S[i][m] = sum_{s in class i} coef[m][s] K_s (local memory)
+            for (int r = 0; r < 2; ++r) {
+                row[r] = st * kERows + slot0 + r * 128;
+                live[r] = row[r] < A.n;
+                const double qn = e_pack_row<T, true>(A, X, row[r], live[r], sA, 2 * hsel + r, rt, nf, xp[r]);
+                const float qnf = __double2float_ru(qn);
+                sq[r] = __fsqrt_ru(qnf);
+                c2row[r] = A.svc_c2 * qnf;
 #pragma unroll
-                for (int m = 0; m < NC1; ++m) { tsum[m] = make_float2(0.f, 0.f); csum[m] = 0.0; }
-                for (int i = 0; i < (NC1 + 1) * NC1; ++i) S[i] = 0.0;
-                int cur_class = A.tile_class[0];
-                for (int j = 0; j < A.n_tiles; ++j, ++g) {
-                    const uint32_t sidx = g % kEStages;
-                    const uint32_t b = g & 1, bph = (g >> 1) & 1;
-                    const int cls = A.tile_class[j];
-                    if (cls != cur_class) {   // uniform across the CTA: support vectors are grouped by class
+                for (int p = 0; p < P; ++p) { decS[p * kERows + slot0 + r * 128] = 0.0; errS[p * kERows + slot0 + r * 128] = 0.f; }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) e_mbar_arrive(aFull);
+
+            // Per (row, coefficient row): FOUR fp32 partial sums per tile (even / odd columns x even / odd groups of four
+            // columns: chains of 16 terms, two FFMA2 accumulators), combined once per tile and added to the class sum with a
+            // compensated (Kahan) fp32 addition -- no fp64 and no F2F in the tile loop (F2F shares the MUFU pipe with ex2).
+            float csum[2][NC1], ccomp[2][NC1];                    // the class being scanned: Kahan sum + compensation
+            float eb[2][NC1];                                     // ... and its error bound, sum_j eta_j |tsum_j|
 #pragma unroll
-                        for (int m = 0; m < NC1; ++m) { S[cur_class * NC1 + m] = csum[m]; csum[m] = 0.0; }
-                        cur_class = cls;
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int m = 0; m < NC1; ++m) { csum[r][m] = 0.f; ccomp[r][m] = 0.f; eb[r][m] = 0.f; }
+            // class `cls` is done: its C-1 sums go to the pairs (cls, opponent), opponent = m < cls ? m : m + 1
+            auto flush_class = [&](int cls) {
+#pragma unroll
+                for (int m = 0; m < NC1; ++m) {
+                    const int o = m < cls ? m : m + 1;
+                    const int i = cls < o ? cls : o, jj = cls < o ? o : cls;
+                    const int p = i * C - (i * (i + 1)) / 2 + (jj - i - 1);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        decS[p * kERows + slot0 + r * 128] += (double)csum[r][m] - (double)ccomp[r][m];
+                        errS[p * kERows + slot0 + r * 128] += eb[r][m];
+                        csum[r][m] = 0.f; ccomp[r][m] = 0.f; eb[r][m] = 0.f;
                     }
-                    e_mbar_wait(&accFull[b], bph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t taddr = tmem_base + lane_addr + (uint32_t)((qt * 2 + b) * kEN);
-                    uint32_t va[16], vb[16];
-                    e_tmem_ld16_issue(taddr, va);
-                    // the coefficients and the tile centre were written by the bulk copy (async proxy): observe ITS barrier
-                    // before reading them (already complete here -- the MMAs consumed the same stage -- so this never blocks)
-                    e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
-                    const float *coef = reinterpret_cast<const float *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
-                    const float4 *ctr = reinterpret_cast<const float4 *>(coef + NC1 * kEN);
-                    float xn = 0.f;   // ||x - c_j||^2 summed directly in fp32: relative error 1e-7 of itself
+                }
+            };
+            int cur_class = A.tile_class[0];
+#pragma unroll 1
+            for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                const uint32_t sidx = g % kEStages;
+                const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                const int cls = A.tile_class[j];
+                if (cls != cur_class) { flush_class(cur_class); cur_class = cls; }   // uniform: support vectors are grouped by class
+                e_mbar_wait(&accFull[b], bph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(((2 * hsel) * 2 + b) * kEN);
+                const uint32_t taddr1 = taddr0 + 2 * kEN;          // the second row's query tile
+                // accumulator columns arrive in chunks of 8 per row, double-buffered (32 registers)
+                uint32_t va0[8], va1[8], vb0[8], vb1[8];
+                e_tmem_ld8_issue(taddr0, va0);
+                e_tmem_ld8_issue(taddr1, va1);
+                // the coefficients and the tile header were written by the bulk copy (async proxy): observe ITS barrier
+                // before reading them (already complete here -- the MMAs consumed the same stage -- so this never blocks)
+                e_mbar_wait(&fullB[sidx], (g / kEStages) & 1);
+                const float *coef = reinterpret_cast<const float *>(sB + (size_t)sidx * A.tile_bytes + kETileB);
+                const float4 *hdr = reinterpret_cast<const float4 *>(coef + NC1 * kEN);   // c'_j [12], eta constants
+                float xn[2] = {0.f, 0.f};   // ||x' - c'_j||^2 summed directly in fp32
 #pragma unroll
-                    for (int j4 = 0; j4 < kEMaxD / 4; ++j4) {
-                        const float4 c = ctr[j4];
+                for (int j4 = 0; j4 < kEMaxD / 4; ++j4) {
+                    const float4 c = hdr[j4];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
                         float t;
-                        t = x32[j4 * 4 + 0] - c.x; xn = fmaf(t, t, xn);
-                        t = x32[j4 * 4 + 1] - c.y; xn = fmaf(t, t, xn);
-                        t = x32[j4 * 4 + 2] - c.z; xn = fmaf(t, t, xn);
-                        t = x32[j4 * 4 + 3] - c.w; xn = fmaf(t, t, xn);
+                        t = xp[r][j4 * 4 + 0] - c.x; xn[r] = fmaf(t, t, xn[r]);
+                        t = xp[r][j4 * 4 + 1] - c.y; xn[r] = fmaf(t, t, xn[r]);
+                        t = xp[r][j4 * 4 + 2] - c.z; xn[r] = fmaf(t, t, xn[r]);
+                        t = xp[r][j4 * 4 + 3] - c.w; xn[r] = fmaf(t, t, xn[r]);
                     }
-                    const float bias = g2 * xn;                        // e = g2 * (acc + ||x - c_j||^2)
-                    auto chunk = [&](const uint32_t (&v)[16], int col0) {
+                }
+                const float4 ec = hdr[3];   // .x = gamma (2 eps_mma + 2^-23) r_j, .y = gamma eps_mma m0_j + eta_const
+                float bias[2], eta[2];
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            float4 cf[NC1];
+                for (int r = 0; r < 2; ++r) {
+                    bias[r] = g2 * xn[r];                           // e = g2 * (acc + ||x' - c'_j||^2)
+                    eta[r] = fmaf(ec.x, sq[r], ec.y) + fmaf(A.svc_c1, xn[r], c2row[r]);
+                }
+                const float2 g22 = make_float2(g2, g2);
+                const float2 bias2[2] = {make_float2(bias[0], bias[0]), make_float2(bias[1], bias[1])};
+                const uint32_t pat = __float_as_uint(ec.z);   // active coefficient rows: count | row0 << 4 | row1 << 7 | ...
+                float dep = eta[0] + eta[1];
+                auto tile_body = [&](auto na_c) {
+                constexpr int NA = decltype(na_c)::value;
+                int rowoff[NA];                               // float offset of active row i inside the tile's coefficient block
 #pragma unroll
-                            for (int m = 0; m < NC1; ++m)
-                                cf[m] = *reinterpret_cast<const float4 *>(coef + m * kEN + col0 + c4 * 4);
-                            const float k0 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 0]), g2, bias));
-                            const float k1 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 1]), g2, bias));
-                            const float k2 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 2]), g2, bias));
-                            const float k3 = e_ex2(fmaf(__uint_as_float(v[c4 * 4 + 3]), g2, bias));
-                            const float2 k01 = make_float2(k0, k1), k23 = make_float2(k2, k3);
+                for (int i = 0; i < NA; ++i) rowoff[i] = (int)((pat >> (4 + 3 * i)) & 7u) * kEN;
+                float2 tsA[2][NA], tsB[2][NA];                // four chains per (row, active coefficient row): see above
 #pragma unroll
-                            for (int m = 0; m < NC1; ++m) {
-                                e_fma2(tsum[m], make_float2(cf[m].x, cf[m].y), k01);
-                                e_fma2(tsum[m], make_float2(cf[m].z, cf[m].w), k23);
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) { tsA[r][i] = make_float2(0.f, 0.f); tsB[r][i] = make_float2(0.f, 0.f); }
+                // Coefficient rows that are zero on the whole tile are skipped: libsvm models are sparse (a support vector of class c
+                // has a non-zero alpha only in the binary problems it supports; on the bench model 26 % of the (tile, row)
+                // combinations are active once create() has sorted the class's vectors by their non-zero pattern).  The tile header
+                // lists the NA active rows; the body below is instantiated for NA = 1 .. NC1.
+                // One block = 4 support-vector columns x 2 rows: NA broadcast LDS.128 of coefficients, 4 FFMA2 for the
+                // exponents, 8 MUFU.EX2, 4 NA FFMA2 into the chains.  The coefficients of block b + 1 are loaded before block b is
+                // computed (explicit double buffer: shared-memory latency was what the FFMA2s waited for, profiles/r02).
+                auto load_cf = [&](float4 (&cf)[NA], int col) {
+#pragma unroll
+                    for (int m = 0; m < NA; ++m)
+#if defined(TCSDN_EXP_NO_CFLDS)   // experiment build: no coefficient loads
+                        cf[m] = make_float4(0.5f, 0.25f, (float)(rowoff[m] + col), 1.f);
+#else
+                        cf[m] = *reinterpret_cast<const float4 *>(coef + rowoff[m] + col);
+#endif
+                };
+                // exps of one block: K[r][0..3] for the two rows (two FFMA2 + four MUFU.EX2 per row)
+                struct K4 { float2 k01[2], k23[2]; };
+                auto exps = [&](const uint32_t *v0, const uint32_t *v1) {
+                    K4 k;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const uint32_t *v = r == 0 ? v0 : v1;
+                        float2 e01 = bias2[r], e23 = bias2[r];
+                        e_fma2(e01, make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), g22);
+                        e_fma2(e23, make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), g22);
+#if defined(TCSDN_EXP_NO_EX2)   // experiment build: no MUFU (tools/gpu_svc_variants.sh)
+                        k.k01[r] = e01; k.k23[r] = e23;
+#else
+                        k.k01[r] = make_float2(e_ex2(e01.x), e_ex2(e01.y));
+                        k.k23[r] = make_float2(e_ex2(e23.x), e_ex2(e23.y));
+#endif
+                    }
+                    return k;
+                };
+                auto sums = [&](const float4 (&cf)[NA], const K4 &k, bool odd) {
+#pragma unroll
+                    for (int m = 0; m < NA; ++m) {
+                        const float2 cxy = make_float2(cf[m].x, cf[m].y), czw = make_float2(cf[m].z, cf[m].w);
+                        if (odd) {
+                            e_fma2(tsB[0][m], cxy, k.k01[0]); e_fma2(tsB[1][m], cxy, k.k01[1]);
+                            e_fma2(tsB[0][m], czw, k.k23[0]); e_fma2(tsB[1][m], czw, k.k23[1]);
+                        } else {
+                            e_fma2(tsA[0][m], cxy, k.k01[0]); e_fma2(tsA[1][m], cxy, k.k01[1]);
+                            e_fma2(tsA[0][m], czw, k.k23[0]); e_fma2(tsA[1][m], czw, k.k23[1]);
+                        }
+                    }
+                };
+                // Software pipeline, one block deep for BOTH inputs of the FFMA2s: while block b is summed, the coefficients
+                // AND the exponentials of block b + 1 are already on their way (the MUFU queue makes ex2's latency long and
+                // variable: consumers scheduled right behind their MUFU stalled the warp, and with two warps per scheduler a
+                // stalled warp leaves the MUFU unit idle).
+                float4 cfA[NA], cfB[NA];
+                load_cf(cfA, 0);
+                e_tmem_ld8_wait2(va0, va1);
+                e_tmem_ld8_issue(taddr0 + 8, vb0);
+                e_tmem_ld8_issue(taddr1 + 8, vb1);
+                K4 kA = exps(va0, va1), kB;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {           // chunk cc = columns 8 cc .. 8 cc + 7
+                    uint32_t (&c0)[8] = (cc & 1) ? vb0 : va0;
+                    uint32_t (&c1)[8] = (cc & 1) ? vb1 : va1;
+                    uint32_t (&n0)[8] = (cc & 1) ? va0 : vb0;
+                    uint32_t (&n1)[8] = (cc & 1) ? va1 : vb1;
+                    if constexpr (AUDIT) {
+                        // audit: |acc - exact| / M_j for this chunk's pairs -- exact from x' and the tile's packed fp32 pieces, in fp64
+                        const unsigned char *tb = sB + (size_t)sidx * A.tile_bytes;
+                        auto piece = [&](int rr, int k) { return (double)__bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(tb + tile_off(rr, k))); };
+                        const float *cj = reinterpret_cast<const float *>(hdr);
+                        double cn = 0.0;
+                        for (int jj = 0; jj < A.d; ++jj) cn += (double)cj[jj] * (double)cj[jj];
+                        for (int c = 0; c < 8; ++c) {
+                            const int col = 8 * cc + c;
+                            double un = 0.0;
+                            double dot[2] = {0.0, 0.0};
+                            for (int jj = 0; jj < A.d; ++jj) {
+                                const double u = piece(col, kslot(0, jj, A.d)) + piece(col, kslot(1, jj, A.d)) + piece(col, kslot(4, jj, A.d));
+                                un += u * u;
+                                dot[0] += (double)xp[0][jj] * u; dot[1] += (double)xp[1][jj] * u;
+                            }
+                            const double nrm = piece(col, 6 * A.d) + piece(col, 6 * A.d + 1) + piece(col, 6 * A.d + 2);
+                            const double w = piece(col, 6 * A.d + 3) + piece(col, 6 * A.d + 4) + piece(col, 6 * A.d + 5);
+                            if (nrm > 1e29) continue;   // padding row
+                            const double rj = sqrt(un);
+                            for (int r = 0; r < 2; ++r) {
+                                const double exact = nrm + w - 2.0 * dot[r];
+                                const double got = (double)__uint_as_float(r == 0 ? c0[c] : c1[c]);
+                                const double M = rj * (2.0 * (double)sq[r] + rj + 2.0 * sqrt(cn)) + 1e-30;
+                                if (live[r]) atomicMax(reinterpret_cast<int *>(A.maxratio), __float_as_int((float)(fabs(got - exact) / M)));
                             }
                         }
-                    };
-                    e_tmem_ld16_wait(va); e_tmem_ld16_issue(taddr + 16, vb); chunk(va, 0);
-                    e_tmem_ld16_wait(vb); e_tmem_ld16_issue(taddr + 32, va); chunk(vb, 16);
-                    e_tmem_ld16_wait(va); e_tmem_ld16_issue(taddr + 48, vb); chunk(va, 32);
-                    e_tmem_ld16_wait(vb);
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) e_mbar_arrive(&accEmpty[b]);        // TMEM buffer may be overwritten
-                    chunk(vb, 48);
-                    // Release the stage only after every coefficient load has actually been PERFORMED: mbarrier.arrive does
-                    // not wait for outstanding ld.shared (see the file header).  The barrier address is made data-dependent
-                    // on the accumulators that consumed every coefficient, so the arrive cannot issue before the loads return
-                    // (cheaper than a MEMBAR.CTA per tile).
-                    {
-                        float dep = xn;
-#pragma unroll
-                        for (int m = 0; m < NC1; ++m) dep += tsum[m].x + tsum[m].y;
-                        const uint32_t off = (dep == 1.2345e38f) ? 8u : 0u;   // never true for finite sums
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
                     }
-#pragma unroll
-                    for (int m = 0; m < NC1; ++m) { csum[m] += (double)tsum[m].x + (double)tsum[m].y; tsum[m] = make_float2(0.f, 0.f); }
-                }
-#pragma unroll
-                for (int m = 0; m < NC1; ++m) S[cur_class * NC1 + m] = csum[m];
-                if (live) {
-                    constexpr int C = NC1 + 1, P = C * (C - 1) / 2;
-                    int vote[C];
-                    for (int c = 0; c < C; ++c) vote[c] = 0;
-                    int p = 0;
-                    for (int i = 0; i < C; ++i)
-                        for (int jj = i + 1; jj < C; ++jj) {
-                            const double dv = (S[i * NC1 + (jj - 1)] + S[jj * NC1 + i]) - A.rho[p];
-                            if (scores) scores[row * P + p] = dv;
-                            if (dv > 0) ++vote[i]; else ++vote[jj];
-                            ++p;
+                    load_cf(cfB, 8 * cc + 4);
+                    kB = exps(c0 + 4, c1 + 4);              // second half of this chunk
+                    sums(cfA, kA, false);
+                    if (cc < 7) {
+                        e_tmem_ld8_wait2(n0, n1);           // next chunk has landed
+                        if (cc == 6) {                      // ... and it was the last one: the TMEM buffer may be overwritten
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) e_mbar_arrive(&accEmpty[b]);
                         }
-                    int arg = 0;
-                    for (int c = 1; c < C; ++c)
-                        if (vote[c] > vote[arg]) arg = c;
-                    labels[row] = arg;
+                        load_cf(cfA, 8 * cc + 8);
+                        kA = exps(n0, n1);
+                    }
+                    sums(cfB, kB, true);
+                    if (cc < 6) {                           // this chunk's registers are free: fetch the chunk after the next
+                        e_tmem_ld8_issue(taddr0 + 8 * (cc + 2), c0);
+                        e_tmem_ld8_issue(taddr1 + 8 * (cc + 2), c1);
+                    }
                 }
+                // tile sums: combine the four chains of every active row, then Kahan-add to the class sum of the coefficient row it
+                // belongs to (one sign inside a tile: |ts| = sum |coef| K)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) {
+                        const float ts = (tsA[r][i].x + tsA[r][i].y) + (tsB[r][i].x + tsB[r][i].y);
+                        dep += ts;
+                        const float be = eta[r] * fabsf(ts);
+#pragma unroll
+                        for (int m = 0; m < NC1; ++m)
+                            if (rowoff[i] == m * kEN) {               // uniform across the CTA
+                                eb[r][m] += be;
+                                const float y = ts - ccomp[r][m];
+                                const float t = csum[r][m] + y;
+                                ccomp[r][m] = (t - csum[r][m]) - y;
+                                csum[r][m] = t;
+                            }
+                    }
+                };   // tile_body
+                switch (pat & 7u) {
+                    case 1: tile_body(std::integral_constant<int, 1>{}); break;
+                    case 2: if constexpr (NC1 >= 2) { tile_body(std::integral_constant<int, 2>{}); } break;
+                    case 3: if constexpr (NC1 >= 3) { tile_body(std::integral_constant<int, 3>{}); } break;
+                    case 4: if constexpr (NC1 >= 4) { tile_body(std::integral_constant<int, 4>{}); } break;
+                    default: if constexpr (NC1 >= 5) { tile_body(std::integral_constant<int, 5>{}); } break;
+                }
+                // Release the stage only after every coefficient load has actually been PERFORMED: mbarrier.arrive does
+                // not wait for outstanding ld.shared (see the file header).  The barrier address is made data-dependent
+                // on the sums that consumed every coefficient, so the arrive cannot issue before the loads return
+                // (cheaper than a MEMBAR.CTA per tile).
+                {
+                    const uint32_t off = (dep == 1.2345e38f) ? 8u : 0u;   // never true for finite sums
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem(&coefFree[sidx]) + off) : "memory");
+                }
+            }
+            flush_class(cur_class);
+            // ---- vote (sk:svm/src/libsvm/svm.cpp:2887-2897) and certificate
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!live[r]) continue;
+                int vote[C], vmin[C], vunc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) { vote[c] = 0; vmin[c] = 0; vunc[c] = 0; }
+                int p = 0;
+#pragma unroll
+                for (int i = 0; i < C; ++i)
+#pragma unroll
+                    for (int jj = i + 1; jj < C; ++jj) {
+                        const double dv = decS[p * kERows + slot0 + r * 128] - A.rho[p];
+                        const float ep = fmaf(errS[p * kERows + slot0 + r * 128], 1.25f, A.svc_eabs[p]);
+                        const bool unc = !(fabs(dv) > (double)ep);    // NaN / inf bounds land here
+                        if (dv > 0) ++vote[i]; else ++vote[jj];
+                        if (unc) { ++vunc[i]; ++vunc[jj]; }
+                        else if (dv > 0) ++vmin[i];
+                        else ++vmin[jj];
+                        if (scores) scores[row[r] * P + p] = A.svc_mode == 4 ? (double)ep : dv;
+                        ++p;
+                    }
+                int arg = 0;
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (vote[c] > vote[arg]) arg = c;
+                // certified iff no assignment of the uncertain pairs lets another class reach the winner's CERTAIN votes
+                // (a tie goes to the lower class index: first maximum)
+                int wmin = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) wmin = (c == arg) ? vmin[c] : wmin;
+                bool sure = true;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int vmax = vmin[c] + vunc[c];
+                    if (c != arg && (vmax > wmin || (vmax == wmin && c < arg))) sure = false;
+                }
+                labels[row[r]] = (sure || A.svc_mode != 0) ? arg : -1 - arg;
             }
         }
         if (A.flag && nf != nf) atomicOr(A.flag, 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 17) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (warp == kEpi + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 // One reference row into row r of a tile image.  `center` is what the B operand is centred on; `delta` (SVC) is
 // (tile centre - global centre): the scalar 2 delta.u rides in three extra K slots against A's 1.0, which turns the
-// globally centred A operand into a locally centred one: ||u||^2 + 2 delta.u - 2 (x - c0).u = ||u||^2 - 2 (x - c_j).u
-static void pack_row(unsigned char *tile, int r, const double *x, const double *center, const double *delta, int d,
-                     double norm_scale) {
+// globally centred A operand into a locally centred one: ||u||^2 + 2 delta.u - 2 (x - c0).u = ||u||^2 - 2 (x - c_j).u.
+// Returns ||u||^2 of the fp32-rounded row.
+static double pack_row(unsigned char *tile, int r, const double *x, const double *center, const double *delta, int d,
+                       double norm_scale) {
     double nrm = 0.0, w = 0.0;
     float c32[kEMaxD];
     for (int j = 0; j < d; ++j) {
@@ -726,6 +1008,7 @@ static void pack_row(unsigned char *tile, int r, const double *x, const double *
         split3(static_cast<float>(w), h, m, l);
         put(6 * d + 3, h); put(6 * d + 4, m); put(6 * d + 5, l);
     }
+    return nrm;
 }
 
 // kd-style ordering: recursively split on the widest coordinate at the median until <= 64 rows remain, emit leaves in
@@ -783,14 +1066,40 @@ int engine_create(tcsdn_model *m) {
     // SVC = per class (sums are per class), rows re-ordered inside the class for spatial compactness (sums do not
     // care about order), padded to a tile boundary with zero-coefficient rows
     std::vector<int32_t> row0, rows, tclass, order((size_t)nref);
+    std::vector<double> coef;          // SVC: dual coefficients [nc1][nref]
+    std::vector<uint8_t> pattern;      // SVC: per support vector, bit mm set iff coefficient row mm is non-zero
     for (int64_t i = 0; i < nref; ++i) order[(size_t)i] = (int32_t)i;
     if (!svc) {
         for (int64_t r = 0; r < nref; r += kEN) { row0.push_back((int32_t)r); rows.push_back((int32_t)std::min<int64_t>(kEN, nref - r)); tclass.push_back(0); }
     } else {
         std::vector<int32_t> start(m->n_classes + 1);
         TCSDN_CUDA(cudaMemcpy(start.data(), m->d_start, start.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        // inside a class: first by the vector's non-zero coefficient pattern (the kernel skips coefficient rows that are zero
+        // on a whole tile), then spatially compact inside every pattern group
+        coef.resize((size_t)nc1 * nref);
+        TCSDN_CUDA(cudaMemcpy(coef.data(), m->d_coef, coef.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        pattern.resize((size_t)nref);
+        std::vector<uint8_t> sortkey((size_t)nref);
+        for (int64_t i = 0; i < nref; ++i) {
+            uint8_t k = 0;
+            for (int mm = 0; mm < nc1; ++mm) k |= (coef[(size_t)mm * nref + i] != 0.0) ? (uint8_t)(1u << mm) : (uint8_t)0;
+            pattern[(size_t)i] = k;
+        }
         for (int c = 0; c < m->n_classes; ++c) {
-            compact_order(ref, d, order, (size_t)start[c], (size_t)start[c + 1]);
+            // ... but only patterns that fill at least four tiles get a group of their own: splitting a small class into a dozen
+            // half-empty groups costs spatial compactness (the radius r_j of the error bound) and skips nothing
+            int count[256] = {0};
+            for (int i = start[c]; i < start[c + 1]; ++i) ++count[pattern[(size_t)i]];
+            for (int i = start[c]; i < start[c + 1]; ++i)
+                if (count[pattern[(size_t)i]] < 4 * kEN) sortkey[(size_t)i] = 255; else sortkey[(size_t)i] = pattern[(size_t)i];
+            std::stable_sort(order.begin() + start[c], order.begin() + start[c + 1],
+                             [&](int32_t a, int32_t b2) { return sortkey[(size_t)a] < sortkey[(size_t)b2]; });
+            for (size_t lo = (size_t)start[c]; lo < (size_t)start[c + 1];) {
+                size_t hi = lo + 1;
+                while (hi < (size_t)start[c + 1] && sortkey[(size_t)order[hi]] == sortkey[(size_t)order[lo]]) ++hi;
+                compact_order(ref, d, order, lo, hi);
+                lo = hi;
+            }
             for (int r = start[c]; r < start[c + 1]; r += kEN) {
                 row0.push_back(r); rows.push_back(std::min(kEN, start[c + 1] - r)); tclass.push_back(c);
             }
@@ -798,37 +1107,77 @@ int engine_create(tcsdn_model *m) {
     }
     E->n_tiles = (int)row0.size();
     std::vector<unsigned char> img((size_t)E->n_tiles * E->tile_bytes, 0);
-    std::vector<double> coef;
-    if (svc) {
-        coef.resize((size_t)nc1 * nref);
-        TCSDN_CUDA(cudaMemcpy(coef.data(), m->d_coef, coef.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    }
     for (int t = 0; t < E->n_tiles; ++t) {
         unsigned char *tile = img.data() + (size_t)t * E->tile_bytes;
         double tc[kEMaxD], delta[kEMaxD];
-        if (svc) {   // tile centre: the mean of its rows, rounded to fp32 (the epilogue subtracts exactly this value)
+        float *hdr = nullptr;
+        double cnorm = 0.0, rmax2 = 0.0;
+        if (svc) {   // tile centre relative to c0: the mean of its rows minus c0, rounded to fp32 (the epilogue subtracts exactly this)
+            hdr = reinterpret_cast<float *>(tile + kETileB + (size_t)nc1 * kEN * sizeof(float));
             for (int j = 0; j < d; ++j) {
                 double a = 0.0;
                 for (int r = 0; r < rows[t]; ++r) a += ref[(size_t)order[(size_t)(row0[t] + r)] * d + j];
-                tc[j] = (double)static_cast<float>(a / rows[t]);
-                delta[j] = tc[j] - center[j];
+                const float cj = static_cast<float>(a / rows[t] - center[j]);
+                hdr[j] = cj;
+                delta[j] = (double)cj;
+                tc[j] = center[j] + (double)cj;
+                cnorm += (double)cj * (double)cj;
             }
-            float *cp = reinterpret_cast<float *>(tile + kETileB + (size_t)nc1 * kEN * sizeof(float));
-            for (int j = 0; j < 16; ++j) cp[j] = j < d ? static_cast<float>(tc[j]) : 0.f;
+            for (int j = d; j < 16; ++j) hdr[j] = 0.f;
         }
         for (int r = 0; r < kEN; ++r) {
             if (r < rows[t]) {
                 const int32_t src = order[(size_t)(row0[t] + r)];
-                pack_row(tile, r, &ref[(size_t)src * d], svc ? tc : center.data(), svc ? delta : nullptr, d,
-                         svc ? 1.0 : 1.0 - (double)kKappa);
+                const double nrm = pack_row(tile, r, &ref[(size_t)src * d], svc ? tc : center.data(), svc ? delta : nullptr, d,
+                                            svc ? 1.0 : 1.0 - (double)kKappa);
+                rmax2 = std::max(rmax2, nrm);
                 if (svc) {
                     float *cf = reinterpret_cast<float *>(tile + kETileB);
-                    for (int mm = 0; mm < nc1; ++mm) cf[mm * kEN + r] = static_cast<float>(coef[(size_t)mm * nref + src]);
+                    for (int mm = 0; mm < nc1; ++mm) {
+                        const double cv = coef[(size_t)mm * nref + src];
+                        cf[mm * kEN + r] = static_cast<float>(cv);
+                        // libsvm's sign pattern (file header): row mm of a class-c vector faces opponent o = mm < c ? mm : mm + 1
+                        // and is >= 0 iff c < o
+                        const int o = mm < tclass[t] ? mm : mm + 1;
+                        if ((tclass[t] < o) ? (cv < 0.0) : (cv > 0.0)) E->certifiable = false;
+                    }
                 }
             } else {
                 pack_dummy(tile, r, d, !svc);
             }
         }
+        if (svc) {   // constants of eta_j (file header), rounded up
+            const double rj = std::sqrt(rmax2) * (1.0 + 1e-6), cj = std::sqrt(cnorm) * (1.0 + 1e-6);
+            const double eps = (double)kSvcEpsMma, p23 = 1.0 / 8388608.0;
+            hdr[12] = std::nextafterf(static_cast<float>(m->gamma * (2.0 * eps + p23) * rj), INFINITY);
+            hdr[13] = std::nextafterf(static_cast<float>(m->gamma * eps * (rj * rj + 2.0 * cj * rj) + (double)kSvcEtaConst), INFINITY);
+            // active coefficient rows of the tile: count | row0 << 4 | row1 << 7 | ... (bit pattern stored in a float slot)
+            uint32_t mask = 0;
+            for (int r = 0; r < rows[t]; ++r) mask |= pattern[(size_t)order[(size_t)(row0[t] + r)]];
+            if (mask == 0) mask = 1;
+            uint32_t word = 0, na = 0;
+            for (int mm = 0; mm < nc1; ++mm)
+                if (mask & (1u << mm)) { word |= (uint32_t)mm << (4 + 3 * na); ++na; }
+            word |= na;
+            memcpy(&hdr[14], &word, 4);
+            hdr[15] = static_cast<float>(rj);
+        }
+    }
+    if (svc) {
+        // absolute part of E_p: rounding e = g2 d to fp32 costs K a relative ln2 2^-24 |e|; for |e| <= 4 that is inside
+        // eta_const, beyond it |e| 2^-|e| <= 1/4 bounds the ABSOLUTE error of coef K by 1.04e-8 |coef|.  Plus 1e-9 for
+        // the float accumulation of the bound itself, ex2's flush to zero and the fp64 kernel's own distance from libsvm.
+        std::vector<int32_t> start(m->n_classes + 1);
+        TCSDN_CUDA(cudaMemcpy(start.data(), m->d_start, start.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        const int Cn = m->n_classes;
+        int p = 0;
+        for (int i = 0; i < Cn; ++i)
+            for (int jj = i + 1; jj < Cn; ++jj, ++p) {
+                double a = 0.0;
+                for (int sidx = start[i]; sidx < start[i + 1]; ++sidx) a += std::fabs(coef[(size_t)(jj - 1) * nref + sidx]);
+                for (int sidx = start[jj]; sidx < start[jj + 1]; ++sidx) a += std::fabs(coef[(size_t)i * nref + sidx]);
+                E->eabs[p] = std::nextafterf(static_cast<float>(1.04e-8 * a + 1e-9), INFINITY);
+            }
     }
     int rc = upload(&E->d_tiles, img.data(), img.size());
     if (rc == TCSDN_OK && !svc) {   // exact re-evaluation reads the original rows with 16-byte loads: even row stride
@@ -859,40 +1208,50 @@ void engine_destroy(tcsdn_model *m) {
     m->engine = nullptr;
 }
 
-bool engine_usable(const tcsdn_model *m, int64_t n) {
-    if (!m->engine) return false;
+bool engine_usable(const tcsdn_model *m, int64_t n, bool want_scores) {
+    const EngineState *E = static_cast<const EngineState *>(m->engine);
+    if (!E) return false;
+    if (m->kind == TCSDN_KIND_SVC) {
+        if (!E->certifiable) return false;                     // the certificate needs libsvm's coefficient signs
+        if (want_scores != (m->opt_engine >= 3)) return false; // decision values: fp64 kernel; audit modes fill scores
+    } else if (m->opt_engine == 4) return false;
     if (m->opt_engine >= 2) return true;
     return n >= 4096;   // below this the fp64 CUDA-core kernels (latency path) are faster than filling 148 SMs x 512 rows
 }
 
 template <typename T>
-static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                           cudaStream_t st) {
     EngineState *E = static_cast<EngineState *>(m->engine);
     const bool svc = m->kind == TCSDN_KIND_SVC;
     EngineArgs A;
     A.tiles = E->d_tiles; A.tile_class = E->d_tile_class; A.tile_row0 = E->d_tile_row0;
     A.tile_rows = E->d_tile_rows; A.center = E->d_center; A.ref = m->d_fit; A.y = m->d_y; A.rho = m->d_rho;
-    // audit mode (engine option 3): the KNN filter is disabled so that EVERY pair is re-evaluated exactly, and the
-    // largest |tensor-core value - exact| / (||x||^2 + ||t||^2) is recorded (stats[5]); tests only
+    // audit mode (engine option 3): KNN -- the filter is disabled so that EVERY pair is re-evaluated exactly; both -- the
+    // largest |tensor-core value - exact| / (error model's denominator) is recorded (stats[5]); tests only
     A.maxratio = m->opt_engine == 3 ? E->d_maxratio : nullptr;
-    A.flag = m->opt_check_finite ? m->d_flag : nullptr; A.n = n; A.n_tiles = E->n_tiles;
+    A.flag = flag; A.n = n; A.n_tiles = E->n_tiles;
     A.tile_bytes = E->tile_bytes; A.d = m->d; A.k = m->k; A.C = m->n_classes; A.nc1 = E->nc1;
     A.refpad = E->d_refpad; A.dpad = (m->d + 1) & ~1;
-    static int flush_tiles = -1;   // experiment knob: TCSDN_KNN_FLUSH = tiles between two evaluation rounds
-    if (flush_tiles < 0) { const char *e = getenv("TCSDN_KNN_FLUSH"); flush_tiles = e ? std::max(1, std::min(31, atoi(e))) : kEFlushTiles; }
-    A.flush_tiles = flush_tiles;
+    A.flush_tiles = m->opt_knn_flush > 0 ? (int)m->opt_knn_flush : kEFlushTiles;   // TCSDN_OPT_KNN_FLUSH_TILES
     A.n_ref = (int)(svc ? m->n_sv : m->n_train);
     A.g2 = static_cast<float>(-m->gamma * 1.4426950408889634);
+    A.svc_mode = svc && m->opt_engine >= 3 ? (int)m->opt_engine : 0;
+    A.svc_c1 = std::nextafterf(static_cast<float>(m->gamma * (1.0 / 1048576.0 + 1.0 / 16777216.0)), INFINITY);
+    A.svc_c2 = std::nextafterf(static_cast<float>(m->gamma / 16777216.0), INFINITY);
+    for (int p = 0; p < (kEMaxNC1 + 1) * kEMaxNC1 / 2; ++p) A.svc_eabs[p] = E->eabs[p];
     const bool heap_smem = !svc && m->k <= kEHeapSmemK;
+    const int P = m->n_classes * (m->n_classes - 1) / 2;
     const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 +
-                        (svc ? 0 : 512 * (size_t)kEListCap * sizeof(uint16_t)) + (heap_smem ? 512 * (size_t)m->k * 12 : 0);
+                        (svc ? (size_t)P * kERows * (sizeof(double) + sizeof(float))
+                             : 512 * (size_t)kEListCap * sizeof(uint16_t) + (heap_smem ? 512 * (size_t)m->k * 12 : 0));
     const int64_t n_super = (n + kERows - 1) / kERows;
     const unsigned grid = (unsigned)std::min<int64_t>(n_super, m->sm_count);
 #define TCSDN_LAUNCH(SVCF, NC)                                                                                    \
     {                                                                                                             \
-        auto kern = engine_kernel<T, SVCF, NC>;                                                                   \
+        auto kern = (SVCF && A.maxratio) ? engine_kernel<T, SVCF, NC, SVCF> : engine_kernel<T, SVCF, NC, false>;   \
         TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        kern<<<grid, kEThreads, smem, st>>>(A, x, labels, scores, E->d_counters);                                 \
+        kern<<<grid, SVCF ? kESvcThreads : kEKnnThreads, smem, st>>>(A, x, labels, scores, E->d_counters);        \
     }
     if (!svc) {
         const int variant = (heap_smem ? 1 : 0) | (A.maxratio ? 2 : 0);
@@ -909,32 +1268,33 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
         case 3: TCSDN_LAUNCH(true, 3) break;
         case 4: TCSDN_LAUNCH(true, 4) break;
         case 5: TCSDN_LAUNCH(true, 5) break;
-        case 6: TCSDN_LAUNCH(true, 6) break;
-        case 7: TCSDN_LAUNCH(true, 7) break;
         default: set_error("svc engine: unsupported class count"); return TCSDN_EINVAL;
     }
 #undef TCSDN_LAUNCH
     TCSDN_CUDA(cudaGetLastError());
     m->stats[0] += 1;
     m->stats[1] += n;
+    // SVC: rows the certificate could not decide carry -1 - label; the fp64 kernel re-evaluates exactly those (same stream)
+    if (svc && A.svc_mode == 0) return launch_svc_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, E->d_counters, st);
     return TCSDN_OK;
 }
 
-int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores, cudaStream_t st) {
+int launch_engine(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores, int32_t *flag,
+                  cudaStream_t st) {
     if (n == 0) return TCSDN_OK;
-    if (dtype == TCSDN_F32) return launch_engine_t<float>(m, static_cast<const float *>(x), n, labels, scores, st);
-    return launch_engine_t<double>(m, static_cast<const double *>(x), n, labels, scores, st);
+    if (dtype == TCSDN_F32) return launch_engine_t<float>(m, static_cast<const float *>(x), n, labels, scores, flag, st);
+    return launch_engine_t<double>(m, static_cast<const double *>(x), n, labels, scores, flag, st);
 }
 
-// cumulative engine counters since create(): exact re-evaluations, max error ratio * 2^40 (synchronising read)
-void engine_read_stats(const tcsdn_model *m, int64_t *exact_evals, int64_t *maxratio_q40) {
-    *exact_evals = 0; *maxratio_q40 = 0;
+// cumulative engine counters since create() (synchronising read): out[3] exact re-evaluations of the knn filter,
+// out[5] largest audited error ratio * 2^40, out[6] svc rows handed to the fp64 kernel
+void engine_read_stats(const tcsdn_model *m, int64_t *out) {
     EngineState *E = static_cast<EngineState *>(m->engine);
     if (!E) return;
     unsigned long long c = 0;
     float v = 0.f;
-    if (cudaMemcpy(&c, E->d_counters, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) *exact_evals = (int64_t)c;
-    if (cudaMemcpy(&v, E->d_maxratio, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) *maxratio_q40 = (int64_t)((double)v * 1099511627776.0);
+    if (cudaMemcpy(&c, E->d_counters, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) out[m->kind == TCSDN_KIND_SVC ? 6 : 3] = (int64_t)c;
+    if (cudaMemcpy(&v, E->d_maxratio, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (int64_t)((double)v * 1099511627776.0);
 }
 
 }  // namespace tcsdn

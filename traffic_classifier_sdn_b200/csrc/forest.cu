@@ -26,6 +26,7 @@
 // shared-memory wavefronts, and lanes that sit at the same node share one.
 // Trees larger than the buffer are walked in place in HBM/L2.
 // Algorithmic bytes per row: 4*d in + 4 out (+ 8 per node visit).
+#include <cfloat>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -78,7 +79,7 @@ __device__ __forceinline__ void acc_add_one_if(uint32_t smem_addr, bool pred) {
 }
 
 // the index-based walker: trees that do not fit the shared-memory buffer are walked where they lie (HBM / L2)
-template <bool IN_SMEM, int kFThreads, int kRPT>
+template <int kFThreads, int kRPT>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ np, uint32_t halt, const float *xs, double *acc,
                                            const double *leaf_val, int C, int r0, const bool (&alive)[kRPT]) {
     uint32_t pos[kRPT];
@@ -195,7 +196,6 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
     const uint32_t xs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
     const uint32_t acc_addr = static_cast<uint32_t>(__cvta_generic_to_shared(acc));
     const uint32_t snodes_addr = static_cast<uint32_t>(__cvta_generic_to_shared(snodes));
-    __shared__ int32_t s_tb[1];  // placeholder to keep static smem non-empty (tree_base is read from L1)
     __shared__ int s_hist[kFRows];          // coherence sort: bucket counts / cursors
     __shared__ uint16_t s_orig[kFRows];     // coherence sort: slot -> row of the tile
 
@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
             for (int e = tid; e < total; e += kFThreads) {
                 float v = static_cast<float>(src[e]);
                 nf = fmaf(v, 0.f, nf);
-                xs[f * kFRows + r] = v;
+                // non-finite values are recorded in nf (the call fails with TCSDN_ENONFINITE, as sklearn raises) and walk as
+                // 0: a -inf would satisfy `v <= -inf` at a leaf / the halt node and send the chain past the group's end
+                xs[f * kFRows + r] = (fabsf(v) <= FLT_MAX) ? v : 0.f;
                 r += dr; f += df;
                 if (f >= d) { f -= d; r += 1; }
             }
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
                 walk_group_smem<kFThreads, kRPT>(snodes_addr, snodes_addr + (uint32_t)(gn - 1) * 8u, xs_addr, acc_addr, acc,
                                                  A.leaf_val, C, tid, alive);
             else
-                walk_group<false, kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, alive);
+                walk_group<kFThreads, kRPT>(A.nodes + node0, (uint32_t)(gn - 1), xs, acc, A.leaf_val, C, tid, alive);
         }
         // each thread finalises its own rows (only it touched their accumulators)
 #pragma unroll
@@ -335,7 +337,6 @@ __global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_const
         }
     }
     if (flag && nf != nf) atomicOr(flag, 1);
-    (void)s_tb;
 }
 
 static float floor32(double t) {
@@ -474,7 +475,8 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
 }
 
 template <typename T, int kFThreads, int kRPT>
-static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                             cudaStream_t st) {
     static_assert(kFThreads * kRPT == kFRows, "tile geometry");
     auto kern = forest_kernel<T, kFThreads, kRPT>;
     const int64_t fixed = (int64_t)(m->d > m->n_classes + 1 ? m->d : m->n_classes + 1) * kFRows * 4 + (int64_t)(m->n_classes + 1) * kFRows * 8;
@@ -486,34 +488,31 @@ static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *lab
     A.nodes = m->d_nodes; A.tree_base = m->d_tree_base; A.group_begin = m->d_group_begin;
     A.leaf_val = m->d_leaf_val; A.n_trees = m->n_trees; A.n_groups = m->n_groups; A.d = m->d;
     A.C = m->n_classes; A.node_cap = (int)buf_nodes; A.n = n;
-    static int sort = -1;   // experiment knob: TCSDN_FOREST_SORT=0 walks the rows in their original order
-    if (sort < 0) { const char *e = getenv("TCSDN_FOREST_SORT"); sort = e ? atoi(e) : 1; }
-    A.sort = sort && m->n_trees > 1;
+    A.sort = m->opt_forest_sort && m->n_trees > 1;   // TCSDN_OPT_FOREST_SORT = 0 walks the rows in their original order
     int64_t tiles = (n + kFRows - 1) / kFRows;
     int64_t grid = tiles < m->sm_count ? tiles : m->sm_count;
-    kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, m->opt_check_finite ? m->d_flag : nullptr);
+    kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, flag);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
 }
 
 template <typename T>
-static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, cudaStream_t st) {
+static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                           cudaStream_t st) {
     // threads x rows-per-thread.  Measured on the 100-tree sklearn forest (12.5M rows): 256 x 4 -> 3.8e8 rows/s,
     // 512 x 2 -> 6.3e8, 1024 x 1 -> 8.2e8: the walk is a chain of dependent shared-memory loads, and 32 warps hide its
-    // latency better than instruction-level parallelism inside 8 or 16.  TCSDN_FOREST_CFG (0, 1) selects the others.
-    static int cfg = -1;
-    if (cfg < 0) { const char *e = getenv("TCSDN_FOREST_CFG"); cfg = e ? atoi(e) : 2; }
-    if (cfg == 0) return launch_forest_cfg<T, 512, 2>(m, x, n, labels, scores, st);
-    if (cfg == 1) return launch_forest_cfg<T, 256, 4>(m, x, n, labels, scores, st);
-    return launch_forest_cfg<T, 1024, 1>(m, x, n, labels, scores, st);
+    // latency better than instruction-level parallelism inside 8 or 16.  TCSDN_OPT_FOREST_SHAPE (1, 2) selects the others.
+    if (m->opt_forest_shape == 1) return launch_forest_cfg<T, 512, 2>(m, x, n, labels, scores, flag, st);
+    if (m->opt_forest_shape == 2) return launch_forest_cfg<T, 256, 4>(m, x, n, labels, scores, flag, st);
+    return launch_forest_cfg<T, 1024, 1>(m, x, n, labels, scores, flag, st);
 }
 
 int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  cudaStream_t st) {
+                  int32_t *flag, cudaStream_t st) {
     if (n == 0) return TCSDN_OK;
     m->stats[0] += 1;
-    if (dtype == TCSDN_F32) return launch_forest_t<float>(m, static_cast<const float *>(x), n, labels, scores, st);
-    return launch_forest_t<double>(m, static_cast<const double *>(x), n, labels, scores, st);
+    if (dtype == TCSDN_F32) return launch_forest_t<float>(m, static_cast<const float *>(x), n, labels, scores, flag, st);
+    return launch_forest_t<double>(m, static_cast<const double *>(x), n, labels, scores, flag, st);
 }
 
 }  // namespace tcsdn

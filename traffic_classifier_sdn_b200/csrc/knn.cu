@@ -100,13 +100,12 @@ __global__ void __launch_bounds__(kKnnThreads) knn_exact_kernel(const T *__restr
 }
 
 int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                     cudaStream_t st) {
+                     int32_t *flag, cudaStream_t st) {
     if (n == 0) return TCSDN_OK;
     const size_t smem = ((size_t)m->d * kKnnThreads + (size_t)kKnnTile * m->d) * sizeof(double);
     int64_t blocks = (n + kKnnThreads - 1) / kKnnThreads;
     int64_t cap = (int64_t)m->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    int32_t *flag = m->opt_check_finite ? m->d_flag : nullptr;
     m->stats[0] += 1;
     m->stats[2] += n;
     if (dtype == TCSDN_F32) {

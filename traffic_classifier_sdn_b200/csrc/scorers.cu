@@ -356,10 +356,8 @@ static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labe
     // (Programmatic dependent launch was tried here -- griddepcontrol.wait/launch_dependents with the PDL launch
     // attribute -- and made the 1M-row CUDA-graph step slower, 15.1 vs 11.9 us: early-launched CTAs of the next grid
     // sit on the SMs waiting.  Plain launches it is.)
-    // fp32 pre-pass: GaussianNB, float32 rows, labels only, unless the fp64 kernels are forced (TCSDN_OPT_ENGINE = 1)
-    static int prepass = -1;   // experiment knob: TCSDN_GNB_PREPASS=0 keeps the tiled kernel on its fp64 path
-    if (prepass < 0) { const char *e = getenv("TCSDN_GNB_PREPASS"); prepass = e ? atoi(e) : 1; }
-    unsigned long long *refined = (KIND == KIND_GNB && sizeof(T) == 4 && scores == nullptr && prepass) ? m->d_refined : nullptr;
+    // fp32 pre-pass: GaussianNB, float32 rows, labels only (TCSDN_OPT_ENGINE = 1 routes to the generic fp64 kernel instead)
+    unsigned long long *refined = (KIND == KIND_GNB && sizeof(T) == 4 && scores == nullptr) ? m->d_refined : nullptr;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag, refined);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
@@ -371,11 +369,9 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
     // CTA shape (measured on B200, 1M x 8 GaussianNB / 10M x 12 LogisticRegression, rows/s):
     //   128 threads x 4 rows: 8.3e10 / 1.105e11    256 x 2: 7.9e10 / 1.132e11    256 x 4: 7.7e10 / 9.7e10    128 x 8: 8.3e10 / 7.7e10
     // GaussianNB (fp64-pipe-bound) wants the constants amortised over 4 rows, the HBM-bound max/min scorers want more warps.
-    // TCSDN_SCORER_CFG=0/1 forces 128 x 4 / 256 x 2.
-    static int cfg = -1;
-    if (cfg < 0) { const char *e = getenv("TCSDN_SCORER_CFG"); cfg = e ? atoi(e) : 2; }
+    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 forces 128 x 4 / 256 x 2.
     const int per_sm = sizeof(T) == 4 ? 3 : 2;
-    const bool wide = cfg == 2 ? KIND != KIND_GNB : cfg == 1;
+    const bool wide = m->opt_scorer_shape == 0 ? KIND != KIND_GNB : m->opt_scorer_shape == 2;
     if (wide) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm);
     return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm);
 }
@@ -421,10 +417,9 @@ static int launch_scorer_t(tcsdn_model *m, int kind, const T *x, int64_t n, int3
 }
 
 int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  cudaStream_t st) {
+                  int32_t *flag, cudaStream_t st) {
     if (n == 0) return TCSDN_OK;
     int kind = m->kind == TCSDN_KIND_GNB ? KIND_GNB : (m->kind == TCSDN_KIND_KMEANS ? KIND_AFFINE_MIN : KIND_AFFINE_MAX);
-    int32_t *flag = m->opt_check_finite ? m->d_flag : nullptr;
     m->stats[0] += 1;
     if (dtype == TCSDN_F32) return launch_scorer_t<float>(m, kind, static_cast<const float *>(x), n, labels, scores, flag, st);
     return launch_scorer_t<double>(m, kind, static_cast<const double *>(x), n, labels, scores, flag, st);

@@ -8,10 +8,12 @@
 //   sk:svm/src/libsvm/libsvm_helper.c:171  rho = -intercept
 //   sk:utils/multiclass.py:557-599      one-vs-rest transform of the OvO values (decision_function)
 //
-// fp64 reference kernel of the path: small batches, and the cross-check of the tensor-core engine.
+// fp64 definition of the path: small batches, every decision_function call, the rows the tensor-core engine's
+// certificate cannot decide, and the engine's cross-check.
 // One thread owns one row; support vectors and their dual coefficients stream through a shared-memory
 // tile (every lane reads the same vector: broadcast).  Support vectors are grouped by class, so the
 // C-1 running sums of the class being scanned stay in registers and are flushed when the class ends.
+// Two kernels: svc_exact_kernel (any d, up to 16 classes) and svc_exact12_kernel (d <= 12, C <= 8: everything in registers).
 #include "common.h"
 
 namespace tcsdn {
@@ -20,24 +22,46 @@ constexpr int kSvcThreads = 128;
 constexpr int kSvcTile = 64;
 constexpr int kSvcMaxC = 16;
 
-template <typename T>
+// MARKED = false: every row.  MARKED = true: only the rows whose label is negative (the tensor-core engine stores
+// -1 - label for rows its certificate could not decide, dist_engine.cu): a CTA scans a chunk of `chunk` labels, compacts
+// the marked rows' offsets into shared memory and runs the same row-per-thread loop over them, so a support-vector tile
+// staged in shared memory still serves up to 128 rows.
+template <typename T, bool MARKED>
 __global__ void __launch_bounds__(kSvcThreads) svc_exact_kernel(const T *__restrict__ X, int64_t n, int d,
                                                                 const double *__restrict__ sv,
                                                                 const double *__restrict__ coef,
                                                                 const double *__restrict__ rho,
                                                                 const int32_t *__restrict__ start, int n_sv, int C,
                                                                 double gamma, int32_t *__restrict__ labels,
-                                                                double *__restrict__ dec_out, int32_t *flag) {
+                                                                double *__restrict__ dec_out, int32_t *flag, int chunk,
+                                                                unsigned long long *counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *xs = reinterpret_cast<double *>(smem_raw);       // [d][kSvcThreads]
     double *ss = xs + (size_t)d * kSvcThreads;               // [kSvcTile][d]
     double *cs = ss + (size_t)kSvcTile * d;                  // [C-1][kSvcTile]
+    uint16_t *list = reinterpret_cast<uint16_t *>(cs + (size_t)(C - 1) * kSvcTile);   // MARKED: [chunk] offsets of marked rows
+    __shared__ int s_cnt;
     const int tid = threadIdx.x;
     const int Cm1 = C - 1;
     float nf = 0.f;
-    for (int64_t r0 = (int64_t)blockIdx.x * kSvcThreads; r0 < n; r0 += (int64_t)gridDim.x * kSvcThreads) {
-        const int64_t row = r0 + tid;
-        const bool live = row < n;
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const int64_t base = ch * chunk;
+        const int cnt = (int)((n - base) < chunk ? (n - base) : chunk);
+        int todo = cnt;
+        if (MARKED) {
+            __syncthreads();
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += kSvcThreads)
+                if (labels[base + i] < 0) list[atomicAdd(&s_cnt, 1)] = (uint16_t)i;   // any order: rows are independent
+            __syncthreads();
+            todo = s_cnt;
+            if (tid == 0 && todo && counter) atomicAdd(counter, (unsigned long long)todo);
+        }
+        for (int g0 = 0; g0 < todo; g0 += kSvcThreads) {
+        const bool live = g0 + tid < todo;
+        const int64_t row = base + (live ? (MARKED ? (int)list[g0 + tid] : g0 + tid) : 0);
         __syncthreads();
         if (live) {
             for (int j = 0; j < d; ++j) {
@@ -104,6 +128,134 @@ __global__ void __launch_bounds__(kSvcThreads) svc_exact_kernel(const T *__restr
                 if (vote[c] > vote[arg]) arg = c;
             labels[row] = arg;
         }
+        }
+    }
+    if (flag && nf != nf) atomicOr(flag, 1);
+}
+
+// The same definition for the common shape (d <= 12, C <= 8): the row lives in registers, a tile of 64 support vectors is
+// staged as [64][12] (zero padded) and read with broadcast 16-byte loads, classes are walked by a compile-time loop so that
+// the C-1 running sums and the C(C-1)/2 decision values stay in registers (no local memory: the generic kernel above keeps
+// S[16][15] on the stack).  Per pair: 24 fp64 operations for the distance, exp(), C-1 DFMA -- bound by the fp64 pipe, not
+// by shared-memory loads (the generic kernel issues 29 of them per pair).  Summation order as in the generic kernel.
+template <typename T, bool MARKED, int C>
+__global__ void __launch_bounds__(kSvcThreads) svc_exact12_kernel(const T *__restrict__ X, int64_t n, int d,
+                                                                  const double *__restrict__ sv,
+                                                                  const double *__restrict__ coef,
+                                                                  const double *__restrict__ rho,
+                                                                  const int32_t *__restrict__ start, int n_sv, double gamma,
+                                                                  int32_t *__restrict__ labels, double *__restrict__ dec_out,
+                                                                  int32_t *flag, int chunk, unsigned long long *counter) {
+    constexpr int D = 12, Cm1 = C - 1, P = C * (C - 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ss = reinterpret_cast<double *>(smem_raw);            // [kSvcTile][D]
+    double *cs = ss + (size_t)kSvcTile * D;                       // [kSvcTile][8]: the vector's C-1 coefficients, padded
+    uint16_t *list = reinterpret_cast<uint16_t *>(cs + (size_t)kSvcTile * 8);   // MARKED: [chunk] offsets of marked rows
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
+    float nf = 0.f;
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const int64_t base = ch * chunk;
+        const int cnt = (int)((n - base) < chunk ? (n - base) : chunk);
+        int todo = cnt;
+        if (MARKED) {
+            __syncthreads();
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += kSvcThreads)
+                if (labels[base + i] < 0) list[atomicAdd(&s_cnt, 1)] = (uint16_t)i;   // any order: rows are independent
+            __syncthreads();
+            todo = s_cnt;
+            if (tid == 0 && todo && counter) atomicAdd(counter, (unsigned long long)todo);
+        }
+        for (int g0 = 0; g0 < todo; g0 += kSvcThreads) {
+            const bool live = g0 + tid < todo;
+            const int64_t row = base + (live ? (MARKED ? (int)list[g0 + tid] : g0 + tid) : 0);
+            double x[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                x[j] = 0.0;
+                if (j < d && live) {
+                    const T v = X[row * d + j];
+                    nf += static_cast<float>(v * static_cast<T>(0));
+                    x[j] = static_cast<double>(v);
+                }
+            }
+            double dec[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) dec[p] = 0.0;
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+                double acc[Cm1];
+#pragma unroll
+                for (int mm = 0; mm < Cm1; ++mm) acc[mm] = 0.0;
+                const int s_begin = start[ci], s_end = start[ci + 1];
+                for (int s0 = s_begin; s0 < s_end; s0 += kSvcTile) {
+                    const int tn = (s_end - s0) < kSvcTile ? (s_end - s0) : kSvcTile;
+                    __syncthreads();
+                    for (int e = tid; e < tn * D; e += kSvcThreads) {
+                        const int tt = e / D, j = e - tt * D;
+                        ss[e] = j < d ? sv[(size_t)(s0 + tt) * d + j] : 0.0;
+                    }
+                    for (int e = tid; e < tn * 8; e += kSvcThreads) {
+                        const int tt = e >> 3, mm = e & 7;
+                        cs[e] = mm < Cm1 ? coef[(size_t)mm * n_sv + s0 + tt] : 0.0;
+                    }
+                    __syncthreads();
+                    if (live) {
+                        for (int tt = 0; tt < tn; ++tt) {
+                            const double2 *sp = reinterpret_cast<const double2 *>(ss + tt * D);
+                            double sum = 0.0;
+#pragma unroll
+                            for (int j2 = 0; j2 < D / 2; ++j2) {
+                                const double2 t = sp[j2];
+                                double df = x[2 * j2] - t.x;
+                                sum = fma(df, df, sum);
+                                df = x[2 * j2 + 1] - t.y;
+                                sum = fma(df, df, sum);
+                            }
+                            const double kv = exp(-gamma * sum);
+                            const double2 *cp = reinterpret_cast<const double2 *>(cs + tt * 8);
+#pragma unroll
+                            for (int m2 = 0; m2 < (Cm1 + 1) / 2; ++m2) {
+                                const double2 c2 = cp[m2];
+                                acc[2 * m2] = fma(c2.x, kv, acc[2 * m2]);
+                                if (2 * m2 + 1 < Cm1) acc[2 * m2 + 1] = fma(c2.y, kv, acc[2 * m2 + 1]);
+                            }
+                        }
+                    }
+                }
+                // class ci is done: row mm belongs to the pair (ci, opponent), opponent = mm < ci ? mm : mm + 1; the lower
+                // class of a pair is scanned first, so dec[p] = (0 + S_lower) + S_upper as in the generic kernel
+#pragma unroll
+                for (int mm = 0; mm < Cm1; ++mm) {
+                    const int o = mm < ci ? mm : mm + 1;
+                    const int i = ci < o ? ci : o, jj = ci < o ? o : ci;
+                    dec[i * C - (i * (i + 1)) / 2 + (jj - i - 1)] += acc[mm];
+                }
+            }
+            if (live) {
+                int vote[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) vote[c] = 0;
+                int p = 0;
+#pragma unroll
+                for (int i = 0; i < C; ++i)
+#pragma unroll
+                    for (int j = i + 1; j < C; ++j) {
+                        const double dv = dec[p] - rho[p];
+                        if (dec_out) dec_out[row * P + p] = dv;
+                        if (dv > 0) ++vote[i]; else ++vote[j];
+                        ++p;
+                    }
+                int arg = 0;
+#pragma unroll
+                for (int c = 1; c < C; ++c)
+                    if (vote[c] > vote[arg]) arg = c;
+                labels[row] = arg;
+            }
+        }
     }
     if (flag && nf != nf) atomicOr(flag, 1);
 }
@@ -137,33 +289,69 @@ int launch_ovr_from_ovo(const double *dec, int64_t n, int C, double *out, cudaSt
     return TCSDN_OK;
 }
 
-int launch_svc_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                     cudaStream_t st) {
-    if (n == 0) return TCSDN_OK;
-    if (m->n_classes > kSvcMaxC) { set_error("svc: more than %d classes", kSvcMaxC); return TCSDN_EINVAL; }
-    const size_t smem = ((size_t)m->d * kSvcThreads + (size_t)kSvcTile * m->d + (size_t)(m->n_classes - 1) * kSvcTile) *
-                        sizeof(double);
-    int64_t blocks = (n + kSvcThreads - 1) / kSvcThreads;
-    int64_t cap = (int64_t)m->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    int32_t *flag = m->opt_check_finite ? m->d_flag : nullptr;
-    m->stats[0] += 1;
-    m->stats[2] += n;
-    if (dtype == TCSDN_F32) {
-        auto kern = svc_exact_kernel<float>;
-        TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kSvcThreads, smem, st>>>(static_cast<const float *>(x), n, m->d, m->d_sv, m->d_coef,
-                                                          m->d_rho, m->d_start, m->n_sv, m->n_classes, m->gamma,
-                                                          labels, scores, flag);
-    } else {
-        auto kern = svc_exact_kernel<double>;
-        TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)blocks, kSvcThreads, smem, st>>>(static_cast<const double *>(x), n, m->d, m->d_sv, m->d_coef,
-                                                          m->d_rho, m->d_start, m->n_sv, m->n_classes, m->gamma,
-                                                          labels, scores, flag);
-    }
+template <typename T, bool MARKED, int C>
+static int launch_svc12(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                        unsigned long long *counter, int chunk, int64_t blocks, cudaStream_t st) {
+    auto kern = svc_exact12_kernel<T, MARKED, C>;
+    const size_t smem = (size_t)kSvcTile * (12 + 8) * sizeof(double) + (MARKED ? (size_t)chunk * sizeof(uint16_t) : 0);
+    TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, kSvcThreads, smem, st>>>(x, n, m->d, m->d_sv, m->d_coef, m->d_rho, m->d_start, m->n_sv, m->gamma,
+                                                      labels, scores, flag, chunk, counter);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
+}
+
+template <typename T, bool MARKED>
+static int launch_svc_t(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
+                        unsigned long long *counter, cudaStream_t st) {
+    if (m->n_classes > kSvcMaxC) { set_error("svc: more than %d classes", kSvcMaxC); return TCSDN_EINVAL; }
+    // MARKED: a chunk should hold enough marked rows to fill the CTA's threads, yet leave eight chunks per SM in flight (the
+    // walk over the support vectors is a latency chain: occupancy, not lane utilisation, is what it needs)
+    int chunk = kSvcThreads;
+    if (MARKED) {
+        int64_t c = (n + (int64_t)m->sm_count * 8 - 1) / ((int64_t)m->sm_count * 8);
+        c = ((c + 1023) / 1024) * 1024;
+        chunk = (int)(c < 1024 ? 1024 : (c > 32768 ? 32768 : c));
+    }
+    int64_t blocks = (n + chunk - 1) / chunk;
+    const int64_t cap = (int64_t)m->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    m->stats[0] += 1;
+    if (m->d <= 12 && m->n_classes <= 8) {
+        switch (m->n_classes) {
+#define TCSDN_CASE(CC) case CC: return launch_svc12<T, MARKED, CC>(m, x, n, labels, scores, flag, counter, chunk, blocks, st);
+            TCSDN_CASE(2) TCSDN_CASE(3) TCSDN_CASE(4) TCSDN_CASE(5) TCSDN_CASE(6) TCSDN_CASE(7) TCSDN_CASE(8)
+#undef TCSDN_CASE
+        }
+    }
+    const size_t smem = ((size_t)m->d * kSvcThreads + (size_t)kSvcTile * m->d + (size_t)(m->n_classes - 1) * kSvcTile) *
+                        sizeof(double) + (MARKED ? (size_t)chunk * sizeof(uint16_t) : 0);
+    auto kern = svc_exact_kernel<T, MARKED>;
+    TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, kSvcThreads, smem, st>>>(x, n, m->d, m->d_sv, m->d_coef, m->d_rho, m->d_start, m->n_sv, m->n_classes,
+                                                      m->gamma, labels, scores, flag, chunk, counter);
+    TCSDN_CUDA(cudaGetLastError());
+    return TCSDN_OK;
+}
+
+template <bool MARKED>
+static int launch_svc_impl(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                           int32_t *flag, unsigned long long *counter, cudaStream_t st) {
+    if (dtype == TCSDN_F32) return launch_svc_t<float, MARKED>(m, static_cast<const float *>(x), n, labels, scores, flag, counter, st);
+    return launch_svc_t<double, MARKED>(m, static_cast<const double *>(x), n, labels, scores, flag, counter, st);
+}
+
+int launch_svc_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                     int32_t *flag, cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    m->stats[2] += n;
+    return launch_svc_impl<false>(m, x, n, dtype, labels, scores, flag, nullptr, st);
+}
+
+int launch_svc_marked(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, unsigned long long *counter,
+                      cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    return launch_svc_impl<true>(m, x, n, dtype, labels, nullptr, nullptr, counter, st);
 }
 
 }  // namespace tcsdn

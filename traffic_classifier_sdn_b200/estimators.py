@@ -261,13 +261,27 @@ class LogisticRegression(_Base):
         return s[:, 0] if s.shape[1] == 1 else s
 
     def predict_proba(self, X):
-        s = self._scores(X)
-        if s.shape[1] == 1:  # sk:linear_model/_logistic.py: binary -> sigmoid
+        return lr_proba(self._scores(X), bool(self._spec.get("ovr", False)))
+
+
+def lr_proba(s, ovr):
+    """LogisticRegression.predict_proba from the decision values s [n, R] (sk:linear_model/_logistic.py:1595-1625):
+    binary -> sigmoid; multinomial -> softmax; one-vs-rest models -> sigmoids normalised over the classes
+    (sk:linear_model/_base.py:429-451, rows of all-zero sigmoids become uniform)."""
+    with np.errstate(over="ignore"):
+        if s.shape[1] == 1:
             p1 = 1.0 / (1.0 + np.exp(-s[:, 0]))
             return np.column_stack([1.0 - p1, p1])
-        s = s - s.max(axis=1, keepdims=True)  # multinomial -> softmax
-        e = np.exp(s)
-        return e / e.sum(axis=1, keepdims=True)
+        if ovr:
+            p = 1.0 / (1.0 + np.exp(-s))
+            tot = p.sum(axis=1)
+            zero = tot == 0
+            p[zero] = 1.0
+            tot[zero] = p.shape[1]
+            return p / tot[:, None]
+    s = s - s.max(axis=1, keepdims=True)
+    e = np.exp(s)
+    return e / e.sum(axis=1, keepdims=True)
 
 
 class GaussianNB(_Base):

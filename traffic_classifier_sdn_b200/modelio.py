@@ -14,7 +14,8 @@ A "spec" is a plain dict of numpy arrays/scalars with a ``kind`` key:
 =========  ==========================================================================
 kind       keys
 =========  ==========================================================================
-linear     coef [R,d] f64, intercept [R] f64, classes  (R == 1 means binary)
+linear     coef [R,d] f64, intercept [R] f64, classes  (R == 1 means binary), ovr (bool:
+           one-vs-rest probabilities)
 gnb        theta [C,d], var [C,d], class_prior [C], classes
 kmeans     centers [k,d]
 knn        fit_X [n_t,d] f64, y [n_t] int32 (class index), k, classes
@@ -146,8 +147,13 @@ def _tree_arrays(tree):
 def _spec_from_attrs(name: str, o) -> Dict[str, Any]:
     if name == "LogisticRegression":
         coef = _f64(o.coef_)
+        # one-vs-rest models (multi_class='ovr', or 'auto' with the liblinear solver, in the scikit-learn releases that
+        # still had the option) turn scores into probabilities with normalised sigmoids, not a softmax
+        # (sk:linear_model/_base.py:429-451 against sk:linear_model/_logistic.py:1620-1625); labels are the same
+        mc, solver = str(getattr(o, "multi_class", "auto")), str(getattr(o, "solver", "lbfgs"))
+        ovr = mc in ("ovr", "warn") or (mc == "auto" and solver == "liblinear")
         return dict(kind="linear", coef=coef, intercept=_f64(np.broadcast_to(o.intercept_, (coef.shape[0],))),
-                    classes=_classes(o), n_features=coef.shape[1])
+                    classes=_classes(o), n_features=coef.shape[1], ovr=bool(ovr))
     if name == "GaussianNB":
         var = getattr(o, "var_", None)
         if var is None:

@@ -44,13 +44,21 @@ class Communicator:
         self._h = C.c_void_p()
         _lib.check(self._lib.tcsdn_comm_init(self.rank, self.world, C.c_char_p(box[0]), C.byref(self._h)))
 
-    def allgather_labels(self, local, n_block: int):
-        """local: CUDA int32 tensor with <= n_block entries -> CUDA int32 tensor [world * n_block] (short shards padded -1)."""
+    def allgather_labels(self, local, n_block: int, n_classes: "int | None" = None, out=None):
+        """local: CUDA int32 tensor with <= n_block entries -> CUDA int32 tensor [world * n_block] (short shards padded -1).
+        With ``n_classes`` <= 255 the labels cross the wire as bytes (tcsdn_allgather_labels_u8); ``out`` lets the
+        caller keep one result buffer (needed when the call is captured into a CUDA graph)."""
         import torch
-        out = torch.empty(self.world * n_block, dtype=torch.int32, device=local.device)
+        if out is None:
+            out = torch.empty(self.world * n_block, dtype=torch.int32, device=local.device)
         st = torch.cuda.current_stream(local.device).cuda_stream
-        _lib.check(self._lib.tcsdn_allgather_labels(self._h, C.c_void_p(local.data_ptr() if local.numel() else 0),
-                                                    local.numel(), n_block, C.c_void_p(out.data_ptr()), C.c_void_p(st)))
+        lp = C.c_void_p(local.data_ptr() if local.numel() else 0)
+        if n_classes is not None:
+            _lib.check(self._lib.tcsdn_allgather_labels_u8(self._h, lp, local.numel(), n_block, C.c_void_p(out.data_ptr()),
+                                                           int(n_classes), C.c_void_p(st)))
+        else:
+            _lib.check(self._lib.tcsdn_allgather_labels(self._h, lp, local.numel(), n_block, C.c_void_p(out.data_ptr()),
+                                                        C.c_void_p(st)))
         return out
 
     def close(self):
@@ -85,7 +93,7 @@ def predict_sharded(model, X, gather: bool = True, group=None, comm: "Communicat
         return local
     per = -(-n // world)
     if comm is not None and torch.is_tensor(local) and local.is_cuda:
-        return comm.allgather_labels(local.contiguous(), per)[:n]
+        return comm.allgather_labels(local.contiguous(), per, n_classes=len(model.classes_))[:n]
     is_t = torch.is_tensor(local)
     t = local if is_t else torch.from_numpy(np.ascontiguousarray(local))
     pad = torch.zeros(per, dtype=torch.int32, device=t.device)   # equal-sized contributions for the collective
