@@ -31,7 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L2_BYTES = 126 << 20
-WORKLOADS = ("gnb", "gnb_100m", "logistic", "kmeans", "forest", "forest_hbm", "knn", "svc")
+# the arithmetic each kernel computes in (a description, not a precision claim: labels are the fp64 definition's everywhere)
+DTYPES = {"gnb": "f32 certified pre-pass + f64 re-evaluation of uncertified rows", "linear": "f64", "kmeans": "f64",
+          "forest": "f32 compares (exact) + f64 accumulation", "knn": "bf16x3 tensor-core filter + f64 exact re-evaluation",
+          "svc": "bf16x3 tensor-core distances + f32 exp/sums with a certificate + f64 re-evaluation of uncertified rows"}
+OPTIONS = []   # (key, value) pairs for tcsdn_set_option on every estimator the bench creates (--set-option)
+WORKLOADS = ("gnb", "gnb_100m", "logistic", "kmeans", "forest", "forest_hbm", "forest_hbm2", "knn", "svc")
 
 
 # ----------------------------------------------------------------------------- workload definitions
@@ -48,7 +53,7 @@ def build_workload(name, quick=False):
 
 
 _FULL_ROWS = {"gnb": 1_000_000, "gnb_100m": 100_000_000, "logistic": 10_000_000, "kmeans": 10_000_000, "forest": 12_500_000, "forest_hbm": 2_000_000,
-              "knn": 10_000_000, "svc": 10_000_000}
+              "forest_hbm2": 1_000_000, "knn": 10_000_000, "svc": 10_000_000}
 
 
 def _build_workload(name, quick=False):
@@ -98,8 +103,14 @@ def _build_workload(name, quick=False):
     if name == "forest_hbm":
         spec = synth.random_forest_spec(n_trees=100, depth=16, seed=seed + 5, full=True)
         return dict(spec=spec, sk=None, d=12, rows=2_000_000 if not quick else 200_000, bytes_per_row=52, flops_per_row=0,
-                    desc="adversarial forest: 100 complete depth-16 trees (13.1M nodes, 105 MB in HBM), 2M rows",
-                    bound="hbm", cpu_sample_rows=100_000)
+                    desc="adversarial forest: 100 complete depth-16 trees (13.1M nodes, 105 MB: L2-resident), 2M rows",
+                    bound="hbm", cpu_sample_rows=100_000, visits_per_row=100 * 17.0)
+    if name == "forest_hbm2":
+        # the regime the "fraction of HBM peak" target is about: the node array (268 MB) does not fit the 126 MB L2
+        spec = synth.random_forest_spec(n_trees=256 if not quick else 32, depth=16, seed=seed + 6, full=True)
+        return dict(spec=spec, sk=None, d=12, rows=1_000_000 if not quick else 100_000, bytes_per_row=52, flops_per_row=0,
+                    desc="adversarial forest, HBM-resident: 256 complete depth-16 trees (33.6M nodes, 268 MB > 126 MB L2), 1M rows",
+                    bound="hbm", cpu_sample_rows=20_000, visits_per_row=256 * 17.0)
     if name == "knn":
         Xtr, ytr = synth.make_flows(50_000, seed=seed + 2)
         spec = dict(kind="knn", fit_X=Xtr, y=ytr.astype(np.int32), k=5, classes=synth.CLASSES, n_features=12)
@@ -135,18 +146,25 @@ def sklearn_model(w):
 
 
 def synth_rows(n, d, seed, device=None):
-    """n float32 rows: a seeded 1M-row synthetic base resampled with replacement (bootstrap) to n rows."""
+    """n float32 rows: a seeded 1M-row synthetic base resampled with replacement (bootstrap) to n rows.  With a device the
+    base rows are derived ON the GPU by the reference's own feature derivation (synth.make_flows_device ->
+    tcsdn_flow_update); the host variant is the bit-identical closed form."""
     import torch
     from traffic_classifier_sdn_b200 import synth
-    base = synth.make_flows(min(n, 1_000_000), seed=seed, d=d, dtype=np.float32, return_labels=False)
-    if n <= len(base):
-        t = torch.from_numpy(base[:n])
-        return t.to(device) if device is not None else t
-    g = torch.Generator().manual_seed(seed)
-    pick = torch.randint(0, len(base), (n,), generator=g)
+    nb = min(n, 1_000_000)
     if device is not None:
-        return torch.from_numpy(base).to(device)[pick.to(device)].contiguous()
-    return torch.from_numpy(base)[pick].contiguous()
+        base = synth.make_flows_device(nb, seed=seed, d=d, dtype="float32", device=device)
+        if n <= nb:
+            return base
+        g = torch.Generator().manual_seed(seed)
+        pick = torch.randint(0, nb, (n,), generator=g)
+        return base[pick.to(device)].contiguous()
+    base = torch.from_numpy(synth.make_flows(nb, seed=seed, d=d, dtype=np.float32, return_labels=False))
+    if n <= nb:
+        return base
+    g = torch.Generator().manual_seed(seed)
+    pick = torch.randint(0, nb, (n,), generator=g)
+    return base[pick].contiguous()
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -191,6 +209,52 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- measurement
+def ring_size(rows, row_bytes):
+    """distinct batches the timed steps rotate through, so that consecutive steps never find their rows in the 126 MiB L2"""
+    if rows * row_bytes >= L2_BYTES * 1.25:
+        return 1
+    return min(12, max(2, int(np.ceil((L2_BYTES * 1.25) / (rows * row_bytes))) + 1))
+
+
+def make_config(w, world):
+    """the `config` object, identical in the b200 and the reference arm (it describes the workload, not the implementation)"""
+    ring = ring_size(w["rows"], 4 * w["d"])
+    return {"workload": w["desc"], "rows_per_gpu_per_step": w["rows"], "n_features": w["d"],
+            "input": "float32 rows: resident in HBM for `value`, in page-locked host memory for `e2e`",
+            "parallelism": f"row-sharded x{world}: every rank classifies its own rows with its own model replica, no collective on the "
+                           "data path; `value_with_gather` adds the one all-gather of per-shard label vectors (uint8 on the wire)",
+            "l2": (f"{ring} distinct batches rotate ({ring * w['rows'] * 4 * w['d'] >> 20} MiB > 126 MiB L2)" if ring > 1 else
+                   f"one batch of {w['rows'] * 4 * w['d'] >> 20} MiB > 126 MiB L2")}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and so its page-locked staging buffers, first touch) to the NUMA node the GPU hangs off: with
+    eight ranks streaming host rows at once, buffers on the far socket cross the inter-socket link and the root complexes
+    contend (e2e efficiency 0.81 at N = 8 in round 1).  Returns a short description; silently does nothing when the
+    topology is not exposed (containers, single-node hosts)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(os.path.join(path, "numa_node")).read().strip())
+        if node < 0:
+            return "numa_node=-1 (not exposed)"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return f"node {node}: no allowed cpu"
+        os.sched_setaffinity(0, ids)
+        return f"node {node} ({len(ids)} cpus)"
+    except Exception as exc:
+        return f"unavailable ({type(exc).__name__})"
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -215,36 +279,62 @@ def max_over_ranks(x, world, device):
 
 
 def measure_with_gather(w, steps, world, device):
-    """SURVEY 8(e) asks for the N-GPU number with and without the gather: the same per-GPU step followed by ONE
-    all-gather of every rank's int32 labels through the library's communicator (tcsdn_allgather_labels)."""
+    """the N-GPU step WITH the one collective of the path -- every rank classifies its block, then ONE all-gather
+    of the per-shard label vectors puts the full vector on every rank (tcsdn_allgather_labels_u8: class indices travel as
+    bytes).  predict + gather are enqueued on one stream with no host synchronisation and the K steps are captured into
+    ONE CUDA graph, like the gather-free measurement."""
     import torch
     from traffic_classifier_sdn_b200 import from_spec
     from traffic_classifier_sdn_b200.parallel import Communicator
     est = from_spec(w["spec"])
     rows, d = w["rows"], w["d"]
+    n_classes = len(w["spec"]["classes"])
     rank = dist_env()[0]
     x = synth_rows(rows, d, seed=4000 + rank, device=device)
     lab = torch.empty(rows, dtype=torch.int32, device=device)
+    allv = torch.empty(rows * world, dtype=torch.int32, device=device)
     comm = Communicator()
-    for _ in range(3):
-        est.predict_indices(x, out=lab)
-        allv = comm.allgather_labels(lab, rows)
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):                       # warm-up outside the capture (also sizes the communicator's staging buffer)
+            est.predict_indices(x, out=lab)
+            comm.allgather_labels(lab, rows, n_classes=n_classes, out=allv)
     torch.cuda.synchronize()
+    mode = "cuda-graph"
+    graph = None
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(steps):
+                est.predict_indices(x, out=lab)
+                comm.allgather_labels(lab, rows, n_classes=n_classes, out=allv)
+        graph.replay()
+        torch.cuda.synchronize()
+    except Exception as exc:
+        graph, mode = None, f"eager ({type(exc).__name__}: {exc})"
+        torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     torch.cuda.synchronize()
     ev0.record()
-    for _ in range(steps):
-        est.predict_indices(x, out=lab)
-        allv = comm.allgather_labels(lab, rows)
+    if graph is not None:
+        graph.replay()
+    else:
+        for _ in range(steps):
+            est.predict_indices(x, out=lab)
+            comm.allgather_labels(lab, rows, n_classes=n_classes, out=allv)
     ev1.record()
     torch.cuda.synchronize()
     barrier(world)
     ms = max_over_ranks(ev0.elapsed_time(ev1), world, device)
-    assert allv.numel() == rows * world
+    ok = bool(torch.equal(allv[rank * rows:(rank + 1) * rows], lab))   # this rank's block of the gathered vector is its own labels
+    del graph
     comm.close()
     return {"value": rows * world * steps / (ms * 1e-3), "unit": "flow-rows/s", "ms_per_step": ms / steps,
-            "gathered_bytes_per_step": 4 * rows * world, "how": "eager launches (no CUDA graph): predict + ncclAllGather per step"}
+            "gathered_bytes_per_step_per_rank": (1 if n_classes <= 255 else 4) * rows * world, "wire": "uint8" if n_classes <= 255 else "int32",
+            "timed_region": mode, "own_block_matches": ok,
+            "how": "predict + tcsdn_allgather_labels_u8 (pack, ncclAllGather of bytes, unpack) per step on one stream"}
 
 
 def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, clock_probe_s=0.0):
@@ -252,12 +342,13 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     import torch
     from traffic_classifier_sdn_b200 import from_spec
     est = from_spec(w["spec"])
+    for key, val in OPTIONS:          # --set-option K=V (tuning sweeps; defaults are the measured best)
+        est.set_option(key, val)
     rows, d = w["rows"], w["d"]
     row_bytes = 4 * d
-    ring = max(2, int(np.ceil((L2_BYTES * 1.25) / (rows * row_bytes))) + 1) if rows * row_bytes < L2_BYTES * 1.25 else 1
+    ring = ring_size(rows, row_bytes)
     rank = dist_env()[0]
-    batches = [synth_rows(rows, d, seed=1000 + 17 * rank + i, device=device) for i in range(min(ring, 12))]
-    ring = len(batches)
+    batches = [synth_rows(rows, d, seed=1000 + 17 * rank + i, device=device) for i in range(ring)]
     torch.cuda.synchronize()
     lab_dev = torch.empty(rows, dtype=torch.int32, device=device)
     side = torch.cuda.Stream(device=device)
@@ -318,23 +409,36 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     ms = max_over_ranks(ms, world, device)
     value = rows * world * steps / (ms * 1e-3)
 
-    # end to end: pinned host rows -> H2D -> kernels -> D2H labels, through the public estimator call
+    # end to end through the PUBLIC call a user of the reference makes -- labels = model.predict(X) on host rows
+    # (traffic_classifier.py:106): H2D of the rows, kernels, D2H of the class indices and classes_.take (the labels are
+    # materialised as the estimator's classes_ dtype, exactly what the sklearn arm pays for too) inside the timed region.
+    # Three variants: rows in page-locked memory (the headline `value`), the same through predict_indices with a
+    # page-locked int32 result buffer (no label materialisation: what a pipeline that keeps indices would see), and
+    # rows in ordinary pageable memory.
     e2e_steps = max(3, min(steps, 10)) if not extras_light else 3
     host = [torch.empty((rows, d), dtype=torch.float32).pin_memory() for _ in range(min(ring, 3))]
     for h, b in zip(host, batches):
         h.copy_(b)
     host_np = [h.numpy() for h in host]
     lab_host = torch.empty(rows, dtype=torch.int32).pin_memory().numpy()   # page-locked result buffer (out=)
-    est.predict_indices(host_np[0], out=lab_host)
-    barrier(world)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        lab = est.predict_indices(host_np[i % len(host_np)], out=lab_host)
-    t1 = time.perf_counter()
-    e2e_s = max_over_ranks(t1 - t0, world, device)
-    e2e = rows * world * e2e_steps / e2e_s
-    assert lab.shape == (rows,)
+
+    def timed(fn, n_steps):
+        fn(0)                                  # untimed first call (allocations, page faults of result arrays)
+        barrier(world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            out = fn(i)
+        dt = max_over_ranks(time.perf_counter() - t0, world, device)
+        assert out.shape == (rows,)
+        return rows * world * n_steps / dt
+
+    e2e_predict = timed(lambda i: est.predict(host_np[i % len(host_np)]), e2e_steps)
+    e2e_indices = timed(lambda i: est.predict_indices(host_np[i % len(host_np)], out=lab_host), e2e_steps)
+    pageable = np.array(host_np[0], copy=True)                            # ordinary (pageable) memory
+    e2e_pageable = timed(lambda i: est.predict(pageable), max(2, e2e_steps // 2))
+    del pageable
+    e2e = e2e_predict
 
     peak = peaks["hbm_gbs"] if w["bound"] == "hbm" else peaks["bf16_tflops"]
     if w["bound"] == "hbm":
@@ -355,40 +459,113 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
         # K = 80 per pair instead of d = 12, reference rows padded to 64-row tiles) and the ncu tensor-pipe figure
         issued = rows * w["issued_mma_flops_per_row"] / (kernel_ms * 1e-3) / 1e12
         roofline.update(issued_mma=issued, issued_mma_frac=issued / peak, tensor_pipe_pct_ncu=load_summary_field(w["name"], "tensor_pipe_pct"))
+        if w.get("exp_per_row"):
+            # SVC is bound by the MUFU unit, not the tensor pipe: one ex2 per (row, support vector) pair against
+            # 16 lanes/clk/SM (measured, tools/tmem_probe.cu) x 148 SMs x the SM clock
+            exp_s = rows * w["exp_per_row"] / (kernel_ms * 1e-3)
+            exp_peak = 16.0 * 148 * (peaks.get("sm_max_mhz") or 1965.0) * 1e6
+            roofline.update(exp_per_s=exp_s, exp_peak=exp_peak, exp_frac=exp_s / exp_peak, xu_pipe_pct_ncu=load_summary_field(w["name"], "xu_pipe_pct"))
     return dict(value=value, ms_per_step=ms / steps, kernel_ms=kernel_ms, rows=rows, ring=ring, mode=mode, traffic=tr,
                 launches_per_step=launches_per_step, load_window=load_window,
-                e2e=dict(value=e2e, unit="flow-rows/s", h2d_bytes_per_step=rows * row_bytes, d2h_bytes_per_step=rows * 4),
+                e2e=dict(value=e2e, unit="flow-rows/s", h2d_bytes_per_step=rows * row_bytes, d2h_bytes_per_step=rows * 4,
+                         call="estimator.predict(X): float32 rows in page-locked host memory -> numpy labels (classes_.take included)",
+                         indices_value=e2e_indices, indices_call="estimator.predict_indices(X, out=page-locked int32): no label materialisation",
+                         pageable_value=e2e_pageable, pageable_call="estimator.predict(X) on rows in pageable host memory",
+                         bound="PCIe: host rows cross at ~48-55 GB/s per GPU; the streaming models' kernels are 50-100x faster than the copy"),
                 roofline=roofline, est=est, batch0=batches[0])
 
 
-def cpu_reference(w, max_seconds=20.0, threads=None):
-    """scikit-learn predict on the host cores, on a bounded sample of the workload's rows."""
+def _threadpools():
+    try:
+        from threadpoolctl import threadpool_info
+        return [{k: p.get(k) for k in ("user_api", "internal_api", "num_threads", "version")} for p in threadpool_info()]
+    except Exception as exc:
+        return [{"error": f"{type(exc).__name__}: {exc}"}]
+
+
+def _svc_pool_predict(sk, X, jobs):
+    """SVC.predict row-chunked over a process pool: libsvm's predict is one serial loop over the rows
+    (sk:svm/src/libsvm/libsvm_helper.c:315-332), so all-core scikit-learn means one chunk per worker process."""
+    from joblib import Parallel, delayed
+    chunks = np.array_split(X, jobs)
+    parts = Parallel(n_jobs=jobs, backend="loky")(delayed(sk.predict)(c) for c in chunks if len(c))
+    return np.concatenate(parts)
+
+
+def cpu_reference(w, max_seconds=20.0, steps=2, warmup=1):
+    """scikit-learn predict on the host cores, on a bounded sample of the workload's rows -- two columns:
+    `as_shipped`: the estimator exactly as the reference's notebooks construct it (defaults: KNN kd_tree with n_jobs=None,
+    RandomForest n_jobs=None, SVC's single-threaded libsvm loop); `value`: best effort on all cores (n_jobs=-1 for
+    RandomForest and KNN, KNN algorithm='brute' = the work the GPU does, SVC row-chunked over a process pool).
+    `warmup` untimed calls, then `steps` timed calls; rows/s = rows * steps / time."""
     import warnings
+    kind = w["spec"]["kind"]
     sk = sklearn_model(w)
     n = min(w["cpu_sample_rows"], w["rows"])
     X = synth_rows(n, w["d"], seed=1000).numpy()
-    if w["spec"]["kind"] not in ("forest",):
+    if kind != "forest":
         X = X.astype(np.float64)   # sklearn validates these estimators to float64 anyway
     cores = os.cpu_count() or 1
-    if hasattr(sk, "n_jobs"):
-        sk.n_jobs = -1
+    jobs = min(cores, 64)
+
+    def run(predict, Xs, budget):
+        """-> (rows/s, rows used): sample shrunk so that warmup + steps calls fit the time budget"""
+        t0 = time.perf_counter()
+        predict(Xs[: max(1, len(Xs) // 20)])
+        probe = (time.perf_counter() - t0) * 20
+        m = len(Xs)
+        if probe * (steps + warmup) > budget:
+            m = max(64, int(m * budget / (probe * (steps + warmup))))
+        Xs = Xs[:m]
+        for _ in range(warmup):
+            predict(Xs)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            predict(Xs)
+        return m * steps / (time.perf_counter() - t0), m
+
+    out = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        t0 = time.perf_counter()
-        sk.predict(X[: max(1, n // 20)])
-        probe = time.perf_counter() - t0
-        if probe * 20 > max_seconds:   # shrink the sample so that the run stays bounded
-            n = max(64, int(n * max_seconds / (probe * 20)))
-            X = X[:n]
-        best = float("inf")
-        for _ in range(2):
-            t0 = time.perf_counter()
-            sk.predict(X)
-            best = min(best, time.perf_counter() - t0)
-    out = dict(value=n / best, unit="flow-rows/s", cores=cores, kind="reference",
-               sample=f"sklearn {type(sk).__name__}.predict on {n} of the workload's rows, best of 2, "
-                      f"{cores} host threads available (n_jobs=-1 where the estimator has it)")
-    if w["spec"]["kind"] == "forest":
+        # ---- as shipped
+        shipped = sk
+        note = "defaults"
+        if kind == "knn":
+            from sklearn.neighbors import KNeighborsClassifier
+            shipped = KNeighborsClassifier(int(w["spec"]["k"])).fit(w["spec"]["fit_X"], w["spec"]["y"])   # algorithm='auto' -> kd_tree
+            note = f"algorithm='auto' -> {shipped._fit_method}, n_jobs=None"
+        elif kind == "forest":
+            sk.n_jobs = None
+            note = "n_jobs=None"
+        elif kind == "svc":
+            note = "single-threaded libsvm loop"
+        v_shipped, m_shipped = run(shipped.predict, X, max_seconds * 0.4)
+        # ---- all cores, best effort
+        if kind == "knn":
+            from sklearn.neighbors import KNeighborsClassifier
+            allc = KNeighborsClassifier(int(w["spec"]["k"]), algorithm="brute", n_jobs=-1).fit(w["spec"]["fit_X"], w["spec"]["y"])
+            v_all, m_all = run(allc.predict, X, max_seconds * 0.6)
+            how = "algorithm='brute' (the GPU's work), n_jobs=-1"
+        elif kind == "forest":
+            sk.n_jobs = -1
+            v_all, m_all = run(sk.predict, X, max_seconds * 0.6)
+            how = "n_jobs=-1"
+        elif kind == "svc":
+            try:
+                Xp = synth_rows(min(w["rows"], max(n, jobs * 400)), w["d"], seed=1000).numpy().astype(np.float64)
+                v_all, m_all = run(lambda Z: _svc_pool_predict(sk, Z, jobs), Xp, max_seconds * 0.6)
+                how = f"rows chunked over a pool of {jobs} processes (joblib/loky)"
+            except Exception as exc:
+                v_all, m_all, how = v_shipped, m_shipped, f"process pool failed ({type(exc).__name__}: {exc}); single thread"
+        else:
+            v_all, m_all, how = v_shipped, m_shipped, "same call (numpy/OpenBLAS/OpenMP use the threads they use: see threadpools)"
+    best, m_best = (v_all, m_all) if v_all >= v_shipped else (v_shipped, m_shipped)
+    out = dict(value=best, unit="flow-rows/s", cores=cores, kind="reference",
+               sample=f"sklearn {type(sk).__name__}.predict on {m_best} of the workload's rows, {warmup} warm-up + {steps} timed calls; "
+                      f"all-core column: {how}",
+               as_shipped=dict(value=v_shipped, rows=m_shipped, how=note), all_cores=dict(value=v_all, rows=m_all, how=how),
+               threadpools=_threadpools())
+    if kind == "forest":
         # SURVEY 8(d): the traversal accounting needs the MEASURED mean number of node visits per row (V-bar)
         try:
             m = min(n, 2000)
@@ -450,7 +627,8 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
-        return dict(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j.get("bf16_tflops", 1590.0)), source="measured")
+        return dict(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j.get("bf16_tflops", 1590.0)), sm_max_mhz=float(j.get("sm_max_mhz", 1965.0)),
+                    source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")
 
 
@@ -462,9 +640,13 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="gnb", choices=WORKLOADS)
     ap.add_argument("--no-extras", action="store_true", help="measure only the headline workload")
-    ap.add_argument("--extras", default="gnb_100m,logistic,kmeans,forest,forest_hbm,knn,svc")
+    ap.add_argument("--extras", default="gnb_100m,logistic,kmeans,forest,forest_hbm,forest_hbm2,knn,svc")
     ap.add_argument("--quick", action="store_true", help="10x smaller batches (debugging)")
+    ap.add_argument("--set-option", action="append", default=[], metavar="KEY=VALUE",
+                    help="tcsdn_set_option on every estimator (include/tcsdn.h TCSDN_OPT_*), e.g. 4=3")
     args = ap.parse_args()
+    for kv in args.set_option:
+        OPTIONS.append((int(kv.split("=")[0]), int(kv.split("=")[1])))
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()
     peaks = load_peaks()
@@ -474,14 +656,14 @@ def main():
             return 0
         w = build_workload(args.workload, args.quick)
         t0 = time.perf_counter()
-        res = cpu_reference(w, max_seconds=max(2.0, 60.0 / (args.steps + args.warmup)))
+        res = cpu_reference(w, max_seconds=90.0, steps=args.steps, warmup=args.warmup)
         wall = time.perf_counter() - t0
         line = {"impl": "reference", "metric": "flow-rows/sec classified (GaussianNB, 1M x 8 synthetic flow rows per GPU)"
                 if args.workload == "gnb" else f"flow-rows/sec classified ({args.workload})",
                 "value": res["value"], "unit": "flow-rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * w["rows"] / res["value"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "rows_per_gpu_per_step": w["rows"], "n_features": w["d"]},
+                "config": make_config(w, args.gpus),
                 "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "flow-rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": wall}
@@ -494,6 +676,7 @@ def main():
         return 1
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
@@ -511,12 +694,12 @@ def main():
                 wx = build_workload(name, args.quick)
                 steps_x = max(3, min(args.steps, 5))
                 r = measure_gpu(wx, steps_x, 3, world, device, peaks, extras_light=True)
-                entry = {"workload": wx["desc"], "value": r["value"], "unit": "flow-rows/s", "rows_per_gpu_per_step": r["rows"],
+                entry = {"workload": wx["desc"], "dtype": DTYPES.get(wx["spec"]["kind"]), "value": r["value"], "unit": "flow-rows/s", "rows_per_gpu_per_step": r["rows"],
                          "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
                          "gpu_launches_per_step": r["launches_per_step"], "engine_stats": r["est"].stats().tolist()}
                 if rank == 0 and world == 1:
                     entry["cpu_baseline"] = cpu_reference(wx, max_seconds=8.0)
-                    vbar = entry["cpu_baseline"].get("node_visits_per_row")
+                    vbar = entry["cpu_baseline"].get("node_visits_per_row") or wx.get("visits_per_row")
                     if vbar:   # forest: rows/s x (52 + 8 V-bar) next to the compulsory-bytes figure
                         tb = r["value"] * (wx["bytes_per_row"] + 8.0 * vbar) / 1e9
                         entry["roofline"].update(traversal_bytes_per_row=wx["bytes_per_row"] + 8.0 * vbar, traversal_achieved=tb,
@@ -540,10 +723,8 @@ def main():
                 if args.workload == "gnb" else f"flow-rows/sec classified ({args.workload})",
                 "value": head["value"], "unit": "flow-rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "rows_per_gpu_per_step": head["rows"], "n_features": w["d"],
-                           "input": "float32 rows resident in HBM", "timed_region": head["mode"], "parallelism": f"row-sharded x{world}, no collective",
-                           "l2": f"{head['ring']} distinct batches rotate ({head['ring'] * head['rows'] * 4 * w['d'] >> 20} MiB > 126 MiB L2)"},
+                "dtype": DTYPES.get(w["spec"]["kind"], "f64"), "data": "synthetic",
+                "config": make_config(w, world), "timed_region": head["mode"], "numa_binding": numa,
                 "e2e": head["e2e"], "gpu_launches": head["launches_per_step"] * args.steps,
                 "roofline": head["roofline"], "kernel_ms": head["kernel_ms"], "clocks": clocks, "models": models}
         if cpu is not None:
@@ -551,7 +732,11 @@ def main():
         if call_pattern is not None:
             line["reference_call_pattern"] = call_pattern
         if gathered is not None:
+            # first-class: the same job with the path's one collective, and how much of the gather-free rate it keeps
             line["with_label_allgather"] = gathered
+            if "value" in gathered:
+                line["value_with_gather"] = gathered["value"]
+                line["gather_efficiency"] = gathered["value"] / head["value"]
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -51,6 +51,44 @@ def test_comm_world1_allgather_pads_short_shard():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_local,n_block,n_classes", [(1000, 1024, 6), (1001, 1001, 6), (997, 1003, 255), (1000, 1024, 300), (0, 8, 3)])
+def test_comm_world1_allgather_u8_wire(n_local, n_block, n_classes):
+    """tcsdn_allgather_labels_u8: labels cross the wire as bytes (n_classes <= 255; wider models fall back to int32), short
+    shards are padded with -1, block lengths that are not multiples of four take the per-rank unpack path; the call is
+    capturable into a CUDA graph once its staging buffer exists"""
+    import torch
+    lib = _lib.load()
+    ident = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    _lib.check(lib.tcsdn_comm_unique_id(ident))
+    h = C.c_void_p()
+    torch.cuda.set_device(0)
+    _lib.check(lib.tcsdn_comm_init(0, 1, ident, C.byref(h)))
+    try:
+        g = torch.Generator().manual_seed(n_local + n_block)
+        local = torch.randint(0, n_classes, (max(n_local, 1),), generator=g, dtype=torch.int32).cuda()[:n_local]
+        out = torch.full((n_block,), 7, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        args = (h, C.c_void_p(local.data_ptr() if n_local else 0), n_local, n_block, C.c_void_p(out.data_ptr()), n_classes)
+        _lib.check(lib.tcsdn_allgather_labels_u8(*args, C.c_void_p(st)))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:n_local], local.cpu().numpy()) and np.all(got[n_local:] == -1)
+        # the same call inside a CUDA graph (no allocation, no host synchronisation on the second call)
+        out.fill_(9)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            _lib.check(lib.tcsdn_allgather_labels_u8(*args, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:n_local], local.cpu().numpy()) and np.all(got[n_local:] == -1)
+    finally:
+        lib.tcsdn_comm_destroy(h)
+
+
+@pytest.mark.gpu
 def test_two_rank_sharded_predict_and_gather():
     import torch
     if torch.cuda.device_count() < 2:

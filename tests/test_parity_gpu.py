@@ -305,11 +305,13 @@ def test_large_batch_properties_scorers_and_forest(specs, models):
 
 
 # ------------------------------------------------------------------ N1: feature derivation on device
-def test_flow_update_kernel_matches_host_formulas():
+def test_flow_update_kernel_matches_oracle():
+    """tcsdn_flow_update against the ORACLE's restatement of Flow.updateforward/updatereverse (traffic_classifier.py:63-96),
+    sample by sample over six polls with repeated timestamps (the `!=` guards) and idle directions"""
     import torch
     from traffic_classifier_sdn_b200 import flows
     rng = np.random.default_rng(5)
-    n = 5000
+    n = 3000
     state = np.zeros((n, flows.STATE))
     t0 = rng.integers(1000, 2000, n).astype(float)
     state[:, flows.T0] = t0
@@ -317,7 +319,7 @@ def test_flow_update_kernel_matches_host_formulas():
     state[:, flows.REV + 8] = t0
     state[:, flows.FWD + 0] = rng.integers(0, 50, n)
     state[:, flows.FWD + 1] = state[:, flows.FWD + 0] * 100
-    host = state.copy()
+    ref = state.copy()
     dstate = torch.from_numpy(state).cuda()
     lib = _lib.load()
     now = t0.copy()
@@ -325,12 +327,12 @@ def test_flow_update_kernel_matches_host_formulas():
         now = now + rng.integers(0, 3, n)   # repeated timestamps hit the `!=` guards
         direction = rng.integers(0, 3, n).astype(np.uint8)
         dp = rng.integers(0, 40, n) * (rng.random(n) < 0.7)
-        cum_p = np.where(direction == 0, host[:, flows.FWD], host[:, flows.REV]) + dp
-        cum_b = np.where(direction == 0, host[:, flows.FWD + 1], host[:, flows.REV + 1]) + dp * rng.integers(60, 1500, n)
+        cum_p = np.where(direction == 0, ref[:, flows.FWD], ref[:, flows.REV]) + dp
+        cum_b = np.where(direction == 0, ref[:, flows.FWD + 1], ref[:, flows.REV + 1]) + dp * rng.integers(60, 1500, n)
         for i in range(n):
             if direction[i] < 2:
-                blk = host[i, flows.REV:flows.REV + 9] if direction[i] else host[i, flows.FWD:flows.FWD + 9]
-                flows.update_direction(blk, host[i, flows.T0], cum_p[i], cum_b[i], now[i])
+                o = flows.REV if direction[i] else flows.FWD
+                ref[i, o:o + 9] = oracle.flow_update(ref[i, o:o + 9], ref[i, flows.T0], cum_p[i], cum_b[i], now[i])
         feats = torch.empty((n, 12), dtype=torch.float64, device="cuda")
         args = [torch.from_numpy(a.astype(np.float64)).cuda() for a in (cum_p, cum_b, now)]
         dd = torch.from_numpy(direction).cuda()
@@ -338,8 +340,42 @@ def test_flow_update_kernel_matches_host_formulas():
                                          dd.data_ptr(), n, feats.data_ptr(), _lib.F64,
                                          torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
-        assert np.array_equal(dstate.cpu().numpy(), host)
-        assert np.array_equal(feats.cpu().numpy(), host[:, flows.FEATURE_COLUMNS])
+        assert np.array_equal(dstate.cpu().numpy(), ref)
+        assert np.array_equal(feats.cpu().numpy(), ref[:, flows.FEATURE_COLUMNS])
+
+
+def test_device_flow_table_equals_host_table(specs):
+    """the CLI's default table (state in HBM, features derived by tcsdn_flow_update) against the host mirror of the
+    reference's run_ryu / Flow (tests/test_host.py checks that mirror against the reference's formulas): state, features
+    and ACTIVE/INACTIVE columns identical after every line, and predict on the device features equals predict on the
+    host features"""
+    from test_host import _monitor_log
+    from traffic_classifier_sdn_b200 import flows
+    host, dev = flows.FlowTable(), flows.DeviceFlowTable()
+    est = from_spec(specs["forest"])
+    for k, line in enumerate(_monitor_log(np.random.default_rng(2), n_flows=40, polls=12)):
+        rec = flows.parse_monitor_line(line)
+        if rec is None:
+            continue
+        host.ingest(rec); dev.ingest(rec)
+        if k % 37 == 0 or k < 5:
+            assert np.array_equal(dev.state, host.state)
+            assert np.array_equal(dev.features(), host.features())
+            assert list(dev.rows()) == list(host.rows())
+    assert np.array_equal(dev.state, host.state) and list(dev.rows()) == list(host.rows())
+    a = est.predict_indices(dev.features_device()).cpu().numpy()
+    assert np.array_equal(a, est.predict_indices(host.features()))
+    assert np.array_equal(a, oracle.predict(specs["forest"], host.features(), want_scores=False)[0])
+
+
+def test_synthetic_rows_through_the_flow_kernel_equal_the_closed_form():
+    """synth.make_flows_device pushes cumulative counters through tcsdn_flow_update poll by poll; the rows must
+    be bit-identical to the closed form the CPU tests use"""
+    from traffic_classifier_sdn_b200 import synth
+    for d, dt in ((12, np.float64), (8, np.float32), (12, np.float32)):
+        ref = synth.make_flows(20_000, seed=11, d=d, dtype=dt, return_labels=False)
+        got = synth.make_flows_device(20_000, seed=11, d=d, dtype="float32" if dt == np.float32 else "float64").cpu().numpy()
+        assert got.dtype == ref.dtype and np.array_equal(got, ref)
 
 
 # ------------------------------------------------------------------ the CLI shim end to end (reference argv words)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Row-sharded predict + the library's NCCL all-gather on W GPUs (run under torchrun; W = WORLD_SIZE).
-Every rank classifies its block, gathers all labels through tcsdn_allgather_labels, and checks them against a
+Every rank classifies its block, gathers all labels through tcsdn_allgather_labels_u8 / tcsdn_allgather_labels, and checks them against a
 full single-GPU predict of the same rows.  Prints 'gather ok' on rank 0."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,7 +21,11 @@ for name, n in (("gnb", 1_000_003), ("forest", 200_001), ("gnb", 5)):
     est = from_spec(w["spec"])
     X = bench.synth_rows(n, w["d"], seed=77, device=dev)
     full = est.predict_indices(X)
-    got = predict_sharded(est, X, gather=True, comm=comm)
+    got = predict_sharded(est, X, gather=True, comm=comm)      # library communicator, labels as bytes on the wire
+    per0 = -(-n // world)
+    a0, b0 = min(n, rank * per0), min(n, (rank + 1) * per0)
+    got32 = comm.allgather_labels(full[a0:b0].contiguous(), per0)[:n]   # the int32 wire format of the same gather
+    ok &= bool(torch.equal(full, got32))
     got_torch = predict_sharded(est, X, gather=True)            # torch.distributed path, same answer
     mine = predict_sharded(est, X, gather=False)
     torch.cuda.synchronize()

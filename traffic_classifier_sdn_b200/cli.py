@@ -17,6 +17,9 @@ Options (none exist in the reference; defaults reproduce it):
     --models DIR        directory holding the six model files (default ``models``)
     --every N           classify every N-th input line (default 10, reference ``:167``)
     --timeout S         training capture length in seconds (default 900, reference ``:27``)
+    --host-features     keep the flow table and its feature derivation on the host (default: the table's state lives in
+                        HBM, ``Flow.updateforward/updatereverse`` run in ``tcsdn_flow_update`` and ``predict`` reads the
+                        features where that kernel wrote them)
 """
 from __future__ import annotations
 
@@ -63,7 +66,12 @@ def classify_table(table: _flows.FlowTable, model):
     """reference printclassifier (:99-118): one row per flow with the predicted traffic type."""
     if len(table) == 0:
         return []
-    labels = model.predict(table.features())   # ONE batched call instead of one per flow
+    if hasattr(table, "features_device"):      # update -> predict on the GPU: the features never leave HBM
+        idx = model.predict_indices(table.features_device())
+        labels = model._labels_from_indices(idx.cpu().numpy())
+        model.sync_check()
+    else:
+        labels = model.predict(table.features())   # ONE batched call instead of one per flow
     rows = []
     for (fid, src, dst, fwd, rev), lab in zip(table.rows(), labels):
         name = lab
@@ -76,10 +84,11 @@ def classify_table(table: _flows.FlowTable, model):
     return rows
 
 
-def run_monitor(stream, model=None, traffic_type=None, f=None, every=10, out=None, max_lines=None):
+def run_monitor(stream, model=None, traffic_type=None, f=None, every=10, out=None, max_lines=None, device_table=False):
     """reference run_ryu (:144-171) over any binary line stream.  Unlike the reference, which never leaves its
-    loop (``out == ''`` compares bytes to str, :150), this returns at end of stream."""
-    table = _flows.FlowTable()
+    loop (``out == ''`` compares bytes to str, :150), this returns at end of stream.
+    device_table: keep the flow state in HBM and derive the features there (flows.DeviceFlowTable)."""
+    table = _flows.DeviceFlowTable() if device_table else _flows.FlowTable()
     count = 0
     while True:
         line = stream.readline()
@@ -122,6 +131,9 @@ def main(argv=None):
     models_dir = _pop_option(argv, "--models", "models")
     every = int(_pop_option(argv, "--every", 10))
     timeout = int(_pop_option(argv, "--timeout", TIMEOUT))
+    host_features = "--host-features" in argv
+    if host_features:
+        argv.remove("--host-features")
     if len(argv) < 1:
         print("ERROR: Incorrect # of args")
         print()
@@ -167,7 +179,7 @@ def main(argv=None):
     p = subprocess.Popen(monitor_cmd, shell=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          start_new_session=True)
     try:
-        run_monitor(p.stdout, model=model, every=every)
+        run_monitor(p.stdout, model=model, every=every, device_table=not host_features)
     finally:
         try:
             os.killpg(os.getpgid(p.pid), signal.SIGTERM)

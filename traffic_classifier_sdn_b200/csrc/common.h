@@ -82,7 +82,7 @@ struct tcsdn_model {
     int64_t opt_engine = 0;
     int64_t opt_chunk_rows = 0;
     int64_t opt_check_finite = 1;
-    int64_t opt_scorer_shape = 0;    // 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2
+    int64_t opt_scorer_shape = 0;    // 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2, 3 = 128 x 2 (small batches)
     int64_t opt_forest_shape = 0;    // 0 auto (1024 x 1), 1 = 512 x 2, 2 = 256 x 4
     int64_t opt_forest_sort = 1;     // coherence sort on/off
     int64_t opt_knn_flush = 0;       // tiles between two evaluation rounds of the knn engine; 0 = default

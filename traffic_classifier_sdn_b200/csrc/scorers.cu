@@ -369,10 +369,17 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
     // CTA shape (measured on B200, 1M x 8 GaussianNB / 10M x 12 LogisticRegression, rows/s):
     //   128 threads x 4 rows: 8.3e10 / 1.105e11    256 x 2: 7.9e10 / 1.132e11    256 x 4: 7.7e10 / 9.7e10    128 x 8: 8.3e10 / 7.7e10
     // GaussianNB (fp64-pipe-bound) wants the constants amortised over 4 rows, the HBM-bound max/min scorers want more warps.
-    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 forces 128 x 4 / 256 x 2.
+    // Small batches: with 512-row tiles a 1M-row batch is 4.4 tiles per CTA -- the pipeline ramp (first tile) and the tail
+    // (some CTAs own one tile more) are a quarter of the step -- so below 16 tiles per CTA the 256-row shape (128 x 2) is used.
+    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 / 3 forces 128 x 4 / 256 x 2 / 128 x 2.
     const int per_sm = sizeof(T) == 4 ? 3 : 2;
-    const bool wide = m->opt_scorer_shape == 0 ? KIND != KIND_GNB : m->opt_scorer_shape == 2;
-    if (wide) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm);
+    int shape = (int)m->opt_scorer_shape;
+    if (shape == 0) {
+        shape = KIND != KIND_GNB ? 2 : 1;
+        if ((n + 511) / 512 < (int64_t)16 * m->sm_count * per_sm) shape = 3;
+    }
+    if (shape == 2) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm);
+    if (shape == 3) return launch_tiled_cfg<T, D, R, KIND, 128, 2>(m, x, n, labels, scores, flag, st, per_sm + 1);
     return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm);
 }
 

@@ -126,3 +126,108 @@ class FlowTable:
                 v = row[col]
                 vals.append(str(int(v)) if k in ints else repr(float(v)))
             yield "\t".join(vals + [str(traffic_type)]) + "\n"
+
+
+class DeviceFlowTable(FlowTable):
+    """The same table with its state rows in HBM: ``Flow.updateforward / updatereverse`` (reference
+    ``traffic_classifier.py:63-96``) run in ``tcsdn_flow_update`` (csrc/flow.cu), the twelve features of ``:104`` are
+    written by that kernel into a device matrix and ``model.predict_indices`` reads them there -- one report is
+    update -> predict with the features never leaving the GPU.  Flow keying and line parsing stay on the host (row N2).
+
+    The reference applies monitor lines one at a time.  Here samples are queued and applied by one kernel call per batch;
+    a second sample for a flow that already has one queued flushes the queue first, so every flow still sees its samples
+    in order and the state is bit-identical to the host table's (tests/test_parity_gpu.py).  Device memory comes from
+    torch (plumbing); the arithmetic is libtcsdn's."""
+
+    def __init__(self, device=None, feature_dtype=np.float64):
+        import torch
+        from . import _lib
+        super().__init__()
+        self._torch, self._lib = torch, _lib
+        self._dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._fdtype = torch.float32 if np.dtype(feature_dtype) == np.float32 else torch.float64
+        self._dstate = torch.zeros((64, STATE), dtype=torch.float64, device=self._dev)
+        self._feat = None
+        self._pend = {}          # flow index -> (direction, packets, bytes, time)
+        self._new_rows = {}      # flow index -> initial state row (Flow.__init__)
+        self._updated = {}       # flow index -> bit 0 / 1: the forward / reverse direction has had an update
+        self._dirty = True       # features out of date
+
+    # ---- queueing (host, same branch order as FlowTable.ingest)
+    def ingest(self, rec) -> None:
+        t, dp, inport, src, dst, outport, packets, nbytes = rec
+        i = self._index.get((dp, src, dst))
+        d = 0
+        if i is None:
+            i = self._index.get((dp, dst, src))
+            d = 1
+        if i is not None:
+            if i in self._pend or i in self._new_rows:
+                self.flush()
+            self._pend[i] = (d, float(packets), float(nbytes), float(t))
+            self._updated[i] = self._updated.get(i, 0) | (1 << d)
+            self._dirty = True
+            return
+        i = len(self._meta)
+        self._index[(dp, src, dst)] = i
+        self._meta.append((dp, inport, src, dst, outport))
+        row = np.zeros(STATE)
+        row[FWD + 0], row[FWD + 1] = packets, nbytes
+        row[FWD + 8] = row[REV + 8] = row[T0] = t
+        self._new_rows[i] = row
+        self._dirty = True
+
+    def flush(self):
+        """apply the queued samples: new flows' initial rows are copied in, then ONE tcsdn_flow_update over all flows"""
+        torch = self._torch
+        n = len(self._meta)
+        if n > self._dstate.shape[0]:
+            grown = torch.zeros((max(n, 2 * self._dstate.shape[0]), STATE), dtype=torch.float64, device=self._dev)
+            grown[: self._dstate.shape[0]] = self._dstate
+            self._dstate = grown
+        if self._new_rows:
+            idx = torch.tensor(sorted(self._new_rows), dtype=torch.int64, device=self._dev)
+            rows = torch.from_numpy(np.stack([self._new_rows[i] for i in sorted(self._new_rows)])).to(self._dev)
+            self._dstate[idx] = rows
+            self._new_rows.clear()
+        if n == 0:
+            return
+        direction = np.full(n, 2, np.uint8)
+        packets, nbytes, now = np.zeros(n), np.zeros(n), np.zeros(n)
+        for i, (d, p, b, t) in self._pend.items():
+            direction[i], packets[i], nbytes[i], now[i] = d, p, b, t
+        self._pend.clear()
+        if self._feat is None or self._feat.shape[0] < n:
+            self._feat = torch.empty((max(n, self._dstate.shape[0]), 12), dtype=self._fdtype, device=self._dev)
+        args = [torch.from_numpy(a).to(self._dev) for a in (packets, nbytes, now)]
+        dd = torch.from_numpy(direction).to(self._dev)
+        with torch.cuda.device(self._dev):
+            self._lib.check(self._lib.load().tcsdn_flow_update(
+                self._dstate.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(), dd.data_ptr(), n,
+                self._feat.data_ptr(), self._lib.F32 if self._fdtype == torch.float32 else self._lib.F64,
+                torch.cuda.current_stream().cuda_stream))
+        self._dirty = False
+
+    # ---- views
+    def features_device(self):
+        """[n_flows, 12] CUDA tensor in the order of reference :104 (valid until the next ingest)"""
+        if self._dirty or self._pend or self._new_rows:
+            self.flush()
+        return self._feat[: len(self._meta)]
+
+    @property
+    def state(self) -> np.ndarray:
+        self.features_device()
+        return self._dstate[: len(self._meta)].cpu().numpy()
+
+    def features(self, dtype=np.float64) -> np.ndarray:
+        return self.features_device().cpu().numpy().astype(dtype, copy=False)
+
+    def rows(self):
+        st = self.state
+        for i, (dp, _inport, src, dst, _out) in enumerate(self._meta):
+            # a direction keeps its initial status (forward ACTIVE :46, reverse INACTIVE :58) until its first update (:75-78, :93-96)
+            mask = self._updated.get(i, 0)
+            fwd = not (st[i, FWD + 3] == 0 or st[i, FWD + 2] == 0) if mask & 1 else True
+            rev = not (st[i, REV + 3] == 0 or st[i, REV + 2] == 0) if mask & 2 else False
+            yield i, src, dst, "ACTIVE" if fwd else "INACTIVE", "ACTIVE" if rev else "INACTIVE"

@@ -29,7 +29,8 @@ FEATURES_12 = ("dFp", "dFb", "FiPps", "FaPps", "FiBps", "FaBps", "dRp", "dRb", "
 COLUMNS_8 = (0, 1, 3, 5, 6, 7, 9, 11)
 
 
-def _direction(rng, n, pps, bpp, idle, age, burst):
+def _direction(rng, n, pps, bpp, idle, age, burst, raw=False):
+    """-> (delta_p, delta_b, avg_pps, avg_bps), or with raw=True the counters behind them: (hist_p, hist_b, cum_p, cum_b)"""
     if pps <= 0.0:
         z = np.zeros(n)
         return z, z, z, z
@@ -44,17 +45,22 @@ def _direction(rng, n, pps, bpp, idle, age, burst):
     hist_b = np.maximum(hist_b, 0.0)
     cum_p = hist_p + delta_p
     cum_b = hist_b + delta_b
+    if raw:
+        return hist_p, hist_b, cum_p, cum_b
     return delta_p, delta_b, cum_p / age, cum_b / age
 
 
-def make_flows(n: int, seed: int = 0, d: int = 12, dtype=np.float64, class_weights=None, return_labels=True):
-    """n synthetic flow rows -> (X [n,d], y [n] class index into CLASSES).  d is 12 or 8."""
+def make_flows(n: int, seed: int = 0, d: int = 12, dtype=np.float64, class_weights=None, return_labels=True, counters=False):
+    """n synthetic flow rows -> (X [n,d], y [n] class index into CLASSES).  d is 12 or 8.
+    counters=True returns instead the cumulative counters the rows derive from: (C [n, 9], y) with columns
+    age, then per direction (forward, reverse): packets and bytes one poll ago, packets and bytes now -- the input of
+    `make_flows_device`, which pushes them through the reference's own derivation on the GPU."""
     if d not in (8, 12):
         raise ValueError("d must be 12 (the models' feature count) or 8 (BASELINE config 2)")
     rng = np.random.default_rng(seed)
     w = np.full(len(CLASSES), 1.0 / len(CLASSES)) if class_weights is None else np.asarray(class_weights, float)
     y = rng.choice(len(CLASSES), size=n, p=w / w.sum()).astype(np.int32)
-    X = np.empty((n, 12), np.float64)
+    X = np.empty((n, 9 if counters else 12), np.float64)
     age = rng.integers(1, 900, n).astype(np.float64)          # seconds since the flow appeared (15 min captures)
     burst = np.exp(rng.normal(0.0, 0.35, n))                  # per-flow rate heterogeneity
     for ci, name in enumerate(CLASSES):
@@ -64,13 +70,47 @@ def make_flows(n: int, seed: int = 0, d: int = 12, dtype=np.float64, class_weigh
             continue
         fp, fb, rp, rb, idle = _PROFILE[name]
         a, b = age[m], burst[m]
+        if counters:
+            X[m] = np.column_stack((a,) + _direction(rng, k, fp, fb, idle, a, b, raw=True) + _direction(rng, k, rp, rb, idle, a, b, raw=True))
+            continue
         dFp, dFb, FaP, FaB = _direction(rng, k, fp, fb, idle, a, b)
         dRp, dRb, RaP, RaB = _direction(rng, k, rp, rb, idle, a, b)
         X[m] = np.column_stack([dFp, dFb, dFp, FaP, dFb, FaB, dRp, dRb, dRp, RaP, dRb, RaB])
+    if counters:
+        return (X, y) if return_labels else X
     if d == 8:
         X = X[:, COLUMNS_8]
     X = np.ascontiguousarray(X, dtype=dtype)
     return (X, y) if return_labels else X
+
+
+def make_flows_device(n: int, seed: int = 0, d: int = 12, dtype="float32", device=None, class_weights=None):
+    """The same rows as `make_flows`, derived ON THE GPU by the reference's own feature derivation
+    (``Flow.updateforward / updatereverse``, traffic_classifier.py:63-96 -> tcsdn_flow_update, csrc/flow.cu) instead of the
+    closed form: every flow is created at t = 0 with zero counters, polled at t = age - 1 and again at t = age, once per
+    direction.  Bit-identical to `make_flows` (tests/test_parity_gpu.py); returns a CUDA tensor [n, d]."""
+    import torch
+    from . import _lib
+    from .flows import STATE
+    C = make_flows(n, seed=seed, class_weights=class_weights, return_labels=False, counters=True)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    Cd = torch.from_numpy(C).to(dev)
+    age = Cd[:, 0].contiguous()
+    state = torch.zeros((n, STATE), dtype=torch.float64, device=dev)      # Flow.__init__ at t = 0, all counters 0
+    fdt = torch.float32 if str(dtype).endswith("32") else torch.float64
+    feat = torch.empty((n, 12), dtype=fdt, device=dev)
+    lib = _lib.load()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        for direction, base in ((0, 1), (1, 5)):
+            dd = torch.full((n,), direction, dtype=torch.uint8, device=dev)
+            for when, cols in ((age - 1.0, (base, base + 1)), (age, (base + 2, base + 3))):
+                p, b = Cd[:, cols[0]].contiguous(), Cd[:, cols[1]].contiguous()
+                _lib.check(lib.tcsdn_flow_update(state.data_ptr(), p.data_ptr(), b.data_ptr(), when.contiguous().data_ptr(),
+                                                 dd.data_ptr(), n, feat.data_ptr(), _lib.F32 if fdt == torch.float32 else _lib.F64, st))
+    if d == 8:
+        feat = feat[:, list(COLUMNS_8)].contiguous()
+    return feat
 
 
 def _full_tree(rng, depth, d, n_classes, impure, scale):
