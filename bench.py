@@ -642,6 +642,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="measure only the headline workload")
     ap.add_argument("--extras", default="gnb_100m,logistic,kmeans,forest,forest_hbm,forest_hbm2,knn,svc")
     ap.add_argument("--quick", action="store_true", help="10x smaller batches (debugging)")
+    ap.add_argument("--gpu-only", action="store_true", help="skip the scikit-learn baselines (tuning sweeps)")
     ap.add_argument("--set-option", action="append", default=[], metavar="KEY=VALUE",
                     help="tcsdn_set_option on every estimator (include/tcsdn.h TCSDN_OPT_*), e.g. 4=3")
     args = ap.parse_args()
@@ -697,21 +698,21 @@ def main():
                 entry = {"workload": wx["desc"], "dtype": DTYPES.get(wx["spec"]["kind"]), "value": r["value"], "unit": "flow-rows/s", "rows_per_gpu_per_step": r["rows"],
                          "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
                          "gpu_launches_per_step": r["launches_per_step"], "engine_stats": r["est"].stats().tolist()}
-                if rank == 0 and world == 1:
+                if rank == 0 and world == 1 and not args.gpu_only:
                     entry["cpu_baseline"] = cpu_reference(wx, max_seconds=8.0)
-                    vbar = entry["cpu_baseline"].get("node_visits_per_row") or wx.get("visits_per_row")
-                    if vbar:   # forest: rows/s x (52 + 8 V-bar) next to the compulsory-bytes figure
-                        tb = r["value"] * (wx["bytes_per_row"] + 8.0 * vbar) / 1e9
-                        entry["roofline"].update(traversal_bytes_per_row=wx["bytes_per_row"] + 8.0 * vbar, traversal_achieved=tb,
-                                                 traversal_frac=tb / peaks["hbm_gbs"])
+                vbar = (entry.get("cpu_baseline") or {}).get("node_visits_per_row") or wx.get("visits_per_row")
+                if vbar and wx["spec"]["kind"] == "forest":   # rows/s x (52 + 8 V-bar) next to the compulsory-bytes figure
+                    tb = r["value"] * (wx["bytes_per_row"] + 8.0 * vbar) / 1e9
+                    entry["roofline"].update(traversal_bytes_per_row=wx["bytes_per_row"] + 8.0 * vbar, traversal_achieved=tb,
+                                             traversal_frac=tb / peaks["hbm_gbs"])
                 models[name] = entry
                 del r
                 torch.cuda.empty_cache()
             except Exception as exc:  # keep the headline line even if a secondary workload fails
                 models[name] = {"error": f"{type(exc).__name__}: {exc}"}
 
-    cpu = cpu_reference(w, max_seconds=15.0) if (rank == 0 and world == 1) else None
-    call_pattern = per_row_call_pattern(w, head["est"]) if (rank == 0 and world == 1) else None
+    cpu = cpu_reference(w, max_seconds=15.0) if (rank == 0 and world == 1 and not args.gpu_only) else None
+    call_pattern = per_row_call_pattern(w, head["est"]) if (rank == 0 and world == 1 and not args.gpu_only) else None
     gathered = None
     if world > 1:
         try:
@@ -727,6 +728,10 @@ def main():
                 "config": make_config(w, world), "timed_region": head["mode"], "numa_binding": numa,
                 "e2e": head["e2e"], "gpu_launches": head["launches_per_step"] * args.steps,
                 "roofline": head["roofline"], "kernel_ms": head["kernel_ms"], "clocks": clocks, "models": models}
+        vbar = (cpu or {}).get("node_visits_per_row") or w.get("visits_per_row")
+        if vbar and w["spec"]["kind"] == "forest":
+            tb = head["value"] / world * (w["bytes_per_row"] + 8.0 * vbar) / 1e9
+            line["roofline"].update(traversal_bytes_per_row=w["bytes_per_row"] + 8.0 * vbar, traversal_achieved=tb, traversal_frac=tb / peaks["hbm_gbs"])
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if call_pattern is not None:

@@ -67,7 +67,7 @@ enum { /* tcsdn_set_option() keys */
     TCSDN_OPT_CHECK_FINITE = 3, /* 1 (default): fail with TCSDN_ENONFINITE on NaN/inf input */
     /* measurement knobs (defaults are the measured best; tools/gpu_check.sh sweeps them) */
     TCSDN_OPT_SCORER_SHAPE = 4,    /* streaming scorers' CTA shape: 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2, 3 = 128 x 2 */
-    TCSDN_OPT_FOREST_SHAPE = 5,    /* forest CTA shape: 0 = 1024 threads x 1 row, 1 = 512 x 2, 2 = 256 x 4 */
+    TCSDN_OPT_FOREST_SHAPE = 5,    /* forest CTA shape: 0 auto, 1 = 512 threads x 2 rows, 2 = 256 x 4, 3 = 1024 x 1 */
     TCSDN_OPT_FOREST_SORT = 6,     /* 1 (default): re-assign a tile's rows to threads in tree-0 leaf order */
     TCSDN_OPT_KNN_FLUSH_TILES = 7  /* knn engine: reference tiles between two exact-evaluation rounds, 1..31; 0 = default */
 };

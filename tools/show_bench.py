@@ -8,5 +8,6 @@ def row(name, v):
     print(f"{name:11s} value={v['value']:.3e} rows/s  ms/step={v['ms_per_step']:.4f}  roofline={rf.get('achieved',0):.1f} {rf.get('unit','')} "
           f"({100*rf.get('frac',0):.1f}%)  e2e={e.get('value',0):.3e}  cpu={c.get('value',0):.3e} ({c.get('cores','?')} cores)")
 row("HEAD", j)
-print("  clocks:", j.get("clocks"), " launches:", j.get("gpu_launches"), " cfg:", j["config"].get("timed_region"))
+print("  clocks:", j.get("clocks"), " launches:", j.get("gpu_launches"), " timed:", j.get("timed_region"), " numa:", j.get("numa_binding"))
+print("  e2e:", {k: (f"{v:.3e}" if isinstance(v, float) else v) for k, v in j.get("e2e", {}).items() if k.endswith("value")})
 for k, v in j.get("models", {}).items(): row(k, v)

@@ -376,7 +376,7 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
             if (value < 0 || value > 3) { set_error("scorer shape must be 0..3"); return TCSDN_EINVAL; }
             m->opt_scorer_shape = value; return TCSDN_OK;
         case TCSDN_OPT_FOREST_SHAPE:
-            if (value < 0 || value > 2) { set_error("forest shape must be 0..2"); return TCSDN_EINVAL; }
+            if (value < 0 || value > 3) { set_error("forest shape must be 0..3"); return TCSDN_EINVAL; }
             m->opt_forest_shape = value; return TCSDN_OK;
         case TCSDN_OPT_FOREST_SORT: m->opt_forest_sort = value ? 1 : 0; return TCSDN_OK;
         case TCSDN_OPT_KNN_FLUSH_TILES:

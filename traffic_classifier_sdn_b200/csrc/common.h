@@ -83,7 +83,7 @@ struct tcsdn_model {
     int64_t opt_chunk_rows = 0;
     int64_t opt_check_finite = 1;
     int64_t opt_scorer_shape = 0;    // 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2, 3 = 128 x 2 (small batches)
-    int64_t opt_forest_shape = 0;    // 0 auto (1024 x 1), 1 = 512 x 2, 2 = 256 x 4
+    int64_t opt_forest_shape = 0;    // 0 auto (1024 x 1; 512 x 2 when trees are walked in HBM), 1 = 512 x 2, 2 = 256 x 4, 3 = 1024 x 1
     int64_t opt_forest_sort = 1;     // coherence sort on/off
     int64_t opt_knn_flush = 0;       // tiles between two evaluation rounds of the knn engine; 0 = default
     // counters of the last predict; atomics because several host threads may predict on one handle (they then add up)
@@ -117,6 +117,7 @@ struct tcsdn_model {
     int64_t n_nodes = 0;
     int group_node_cap = 0;          // nodes that fit in the smem tree buffer
     int max_group_nodes = 0;
+    bool forest_oversize = false;    // some tree exceeds the shared-memory buffer and is walked in L2 / HBM
 
     // ---- per-handle misc
     int32_t *d_flag = nullptr;       // device error flag (non-finite input)

@@ -183,7 +183,7 @@ __device__ __forceinline__ void walk_group_smem(uint32_t nodes_addr, uint32_t ha
 }
 
 template <typename T, int kFThreads, int kRPT>
-__global__ void __launch_bounds__(kFThreads, 1) forest_kernel(const __grid_constant__ ForestArgs A,
+__global__ void __launch_bounds__(kFThreads, kFThreads <= 512 ? 2 : 1) forest_kernel(const __grid_constant__ ForestArgs A,
                                                               const T *__restrict__ X,
                                                               int32_t *__restrict__ labels,
                                                               double *__restrict__ proba, int32_t *flag) {
@@ -437,6 +437,7 @@ int forest_pack(tcsdn_model *m, const int64_t *tree_offsets, const int32_t *left
         }
         if (group_nodes <= m->group_node_cap && group_nodes > m->max_group_nodes)
             m->max_group_nodes = (int)group_nodes;
+        if (tn > m->group_node_cap) m->forest_oversize = true;   // walked where it lies (L2 / HBM)
         if (nodes.size() > (size_t)INT32_MAX) { set_error("forest: more than 2^31 nodes"); return TCSDN_EINVAL; }
         tree_base.push_back((int32_t)nodes.size());
     }
@@ -490,7 +491,9 @@ static int launch_forest_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *lab
     A.C = m->n_classes; A.node_cap = (int)buf_nodes; A.n = n;
     A.sort = m->opt_forest_sort && m->n_trees > 1;   // TCSDN_OPT_FOREST_SORT = 0 walks the rows in their original order
     int64_t tiles = (n + kFRows - 1) / kFRows;
-    int64_t grid = tiles < m->sm_count ? tiles : m->sm_count;
+    // two CTAs per SM when they fit (512-thread shapes with a small tree buffer): twice the gather chains in flight
+    const int per_sm = (kFThreads <= 512 && 2 * (smem + 8 * 1024) <= 227 * 1024) ? 2 : 1;
+    int64_t grid = tiles < (int64_t)m->sm_count * per_sm ? tiles : (int64_t)m->sm_count * per_sm;
     kern<<<(unsigned)grid, kFThreads, smem, st>>>(A, x, labels, scores, flag);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
@@ -502,7 +505,11 @@ static int launch_forest_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     // threads x rows-per-thread.  Measured on the 100-tree sklearn forest (12.5M rows): 256 x 4 -> 3.8e8 rows/s,
     // 512 x 2 -> 6.3e8, 1024 x 1 -> 8.2e8: the walk is a chain of dependent shared-memory loads, and 32 warps hide its
     // latency better than instruction-level parallelism inside 8 or 16.  TCSDN_OPT_FOREST_SHAPE (1, 2) selects the others.
-    if (m->opt_forest_shape == 1) return launch_forest_cfg<T, 512, 2>(m, x, n, labels, scores, flag, st);
+    // Forests whose trees do not fit the shared-memory buffer are walked in L2 / HBM: there the chain of dependent GLOBAL
+    // gathers wants as many chains in flight per SM as possible -- 512 x 2 with two CTAs per SM (2 048 chains) --
+    // TCSDN_OPT_FOREST_SHAPE = 3 forces 1024 x 1 for them too.
+    if (m->opt_forest_shape == 1 || (m->opt_forest_shape == 0 && m->forest_oversize))
+        return launch_forest_cfg<T, 512, 2>(m, x, n, labels, scores, flag, st);
     if (m->opt_forest_shape == 2) return launch_forest_cfg<T, 256, 4>(m, x, n, labels, scores, flag, st);
     return launch_forest_cfg<T, 1024, 1>(m, x, n, labels, scores, flag, st);
 }

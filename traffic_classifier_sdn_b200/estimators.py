@@ -224,7 +224,20 @@ class _Base:
         return self._labels_from_indices(idx)
 
     def _labels_from_indices(self, idx):
-        return self.classes_.take(idx)
+        """classes_.take(idx) (sk:linear_model/_base.py:423): string class names make this a 4-byte read and a 24-byte write
+        per row -- on a million-row batch more host time than the H2D copy and the kernel together -- so large batches
+        are gathered in slices on a few threads (numpy releases the GIL inside take)."""
+        n = len(idx)
+        if n < (1 << 18):
+            return self.classes_.take(idx)
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        out = np.empty(n, dtype=self.classes_.dtype)
+        workers = max(1, min(16, (os.cpu_count() or 1) // 2, n >> 17))
+        bounds = np.linspace(0, n, workers + 1).astype(np.int64)
+        with ThreadPoolExecutor(workers) as pool:
+            list(pool.map(lambda k: np.take(self.classes_, idx[bounds[k]:bounds[k + 1]], out=out[bounds[k]:bounds[k + 1]]), range(workers)))
+        return out
 
     def _scores(self, X):
         s = self._run(X, True)[1]
