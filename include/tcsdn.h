@@ -183,6 +183,20 @@ int tcsdn_allgather_labels(tcsdn_comm_t *comm, const int32_t *local, int64_t n_l
                            void *cuda_stream);
 int tcsdn_allgather_labels_u8(tcsdn_comm_t *comm, const int32_t *local, int64_t n_local, int64_t n_block, int32_t *all,
                               int32_t n_classes, void *cuda_stream);
+/* The same exchange FUSED into the classification (at most 8 ranks, one NVSwitch domain): every rank owns a buffer of
+ * world slots of `slot_bytes` label bytes; the kernels of tcsdn_predict_gathered store each label, as one byte, into slot
+ * [rank] of EVERY rank's buffer -- the local one and, through CUDA IPC peer mappings over NVLink, the others' -- while the
+ * next rows stream in, and a peer-memory barrier closes the call: when `cuda_stream` reaches its end, *gathered_out
+ * (device, [world][slot_bytes], 0xFF = -1 padding) holds every rank's labels.  LogisticRegression / GaussianNB / KMeans
+ * store from inside their scoring kernel; the other estimators run their kernels and one scatter kernel.  No NCCL call, no
+ * host synchronisation: capturable into a CUDA graph.  Two label buffers alternate between calls, so the vector of call k
+ * stays valid until call k + 2 is enqueued.
+ *   tcsdn_comm_gather_buffer  collective; sizes (or grows) the buffers for blocks of up to n_block rows, exchanges the IPC
+ *                             handles through the communicator; slot_bytes_out = n_block rounded up to 16
+ *   tcsdn_predict_gathered    x [n_local][d] on the device, n_local <= slot_bytes; every rank of the communicator calls it */
+int tcsdn_comm_gather_buffer(tcsdn_comm_t *comm, int64_t n_block, const uint8_t **gathered_out, int64_t *slot_bytes_out);
+int tcsdn_predict_gathered(tcsdn_model_t *m, tcsdn_comm_t *comm, const void *x, int64_t n_local, int32_t d, int32_t x_dtype,
+                           const uint8_t **gathered_out, void *cuda_stream);
 void tcsdn_comm_destroy(tcsdn_comm_t *comm);
 
 /* ---- N1 (next row): Flow.updateforward/updatereverse on device ----------------------------------

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from traffic_classifier_sdn_b200 import _lib
+from conftest import spec_from_golden  # noqa: F401  (fixtures `specs` / `golden` come from conftest)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -86,6 +87,44 @@ def test_comm_world1_allgather_u8_wire(n_local, n_block, n_classes):
         assert np.array_equal(got[:n_local], local.cpu().numpy()) and np.all(got[n_local:] == -1)
     finally:
         lib.tcsdn_comm_destroy(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["gnb", "linear", "forest", "knn"])
+def test_predict_gathered_world1(kind, specs):
+    """tcsdn_predict_gathered on one rank: the fused store path of the scorers and the scatter path of the other estimators
+    fill slot 0 of the peer-memory buffer with the labels as bytes (255 padding), also inside a CUDA graph and across the
+    two alternating label buffers"""
+    import torch
+    import torch.distributed as dist
+    from traffic_classifier_sdn_b200 import from_spec, synth
+    from traffic_classifier_sdn_b200.parallel import Communicator
+    torch.cuda.set_device(0)
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1)
+    est = from_spec(specs[kind])
+    comm = Communicator()
+    try:
+        for n in (5003, 1000):
+            X = torch.from_numpy(synth.make_flows(n, seed=n, return_labels=False).astype(np.float32)).cuda()
+            ref = est.predict_indices(X).cpu().numpy()
+            for rep in range(3):                           # epochs 1, 2, 3: both label buffers
+                got = comm.predict_gathered(est, X)
+                torch.cuda.synchronize()
+                g = got.cpu().numpy()
+                assert g.shape[0] == 1 and g.shape[1] % 16 == 0 and g.shape[1] >= n
+                assert np.array_equal(g[0, :n], ref.astype(np.uint8)) and np.all(g[0, n:] == 255)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            got = comm.predict_gathered(est, X)
+        got.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy()[0, :n], ref.astype(np.uint8))
+    finally:
+        comm.close()
 
 
 @pytest.mark.gpu

@@ -32,6 +32,22 @@ for name, n in (("gnb", 1_000_003), ("forest", 200_001), ("gnb", 5)):
     ok &= bool(torch.equal(full, got)) and bool(torch.equal(full, got_torch)) and got.numel() == n
     per = -(-n // world)
     ok &= bool(torch.equal(mine, full[min(n, rank * per):min(n, (rank + 1) * per)]))
+# the exchange fused into the classification: labels of all ranks land in every rank's peer-memory buffer
+for name, n in (("gnb", 1_000_000), ("forest", 50_001)):
+    w = bench.build_workload(name)
+    est = from_spec(w["spec"])
+    per = -(-n // world)
+    X = bench.synth_rows(per * world, w["d"], seed=99, device=dev)[: n]
+    full = est.predict_indices(X)
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    comm.gather_buffer(per)                     # collective: the same block size on every rank
+    for rep in range(3):
+        got = comm.predict_gathered(est, X[a:b])
+        torch.cuda.synchronize()
+        flat = torch.cat([got[r, : min(per, max(0, n - r * per))] for r in range(world)]).to(torch.int32)
+        ok &= bool(torch.equal(flat, full))
+        pad_ok = all(bool((got[r, min(per, max(0, n - r * per)):] == 255).all()) for r in range(world))
+        ok &= pad_ok
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 comm.close()

@@ -56,6 +56,8 @@ SIGNATURES = {
     "tcsdn_comm_init": (C.c_int, [C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]),
     "tcsdn_allgather_labels": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "tcsdn_allgather_labels_u8": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int32, _vp]),
+    "tcsdn_comm_gather_buffer": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp), _i64p]),
+    "tcsdn_predict_gathered": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_vp), _vp]),
     "tcsdn_comm_destroy": (None, [_vp]),
 }
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.h"
 
@@ -67,6 +68,12 @@ struct tcsdn_comm {
     int64_t pad_cap = 0;
     uint8_t *d_bytes = nullptr; // byte-wide wire format: [n_block] packed local labels, then [world * n_block] gathered
     int64_t bytes_cap = 0;      // in units of n_block
+    // peer-memory exchange (tcsdn_comm_gather_buffer): one allocation per rank = 2 epochs x [world][g_block] label bytes,
+    // then the barrier flags; g_peer[r] = rank r's allocation as seen from this process (CUDA IPC; [rank] = the local one)
+    uint8_t *g_peer[tcsdn::kMaxPeers] = {nullptr};
+    int64_t g_block = 0;        // bytes per rank slot (multiple of 16)
+    int64_t g_bytes = 0;        // label bytes per epoch = world * g_block
+    uint32_t g_epoch = 0;       // calls so far (flags carry it)
 };
 
 namespace tcsdn {
@@ -88,19 +95,59 @@ __global__ void labels_pack_u8(const int32_t *__restrict__ src, int64_t n_src, u
 }
 
 __global__ void labels_unpack_u8(const uint8_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n) {
+    // src is 4-byte aligned (blocks start on 4-byte boundaries); dst may start at any int32 (odd block lengths): scalar stores
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += stride) {
         if (i * 4 + 4 <= n) {
             const uint32_t w = reinterpret_cast<const uint32_t *>(src)[i];
-            int4 o;
-            o.x = (w & 0xFFu) == 0xFFu ? -1 : (int)(w & 0xFFu);
-            o.y = ((w >> 8) & 0xFFu) == 0xFFu ? -1 : (int)((w >> 8) & 0xFFu);
-            o.z = ((w >> 16) & 0xFFu) == 0xFFu ? -1 : (int)((w >> 16) & 0xFFu);
-            o.w = (w >> 24) == 0xFFu ? -1 : (int)(w >> 24);
-            reinterpret_cast<int4 *>(dst)[i] = o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t b = (w >> (8 * k)) & 0xFFu;
+                dst[i * 4 + k] = b == 0xFFu ? -1 : (int32_t)b;
+            }
         } else {
             for (int64_t e = i * 4; e < n; ++e) dst[e] = src[e] == 0xFF ? -1 : (int)src[e];
         }
+    }
+}
+
+// Cross-rank barrier over peer memory: rank writes its epoch into slot [rank] of every rank's flag array (release, system
+// scope: the label bytes this rank stored into the peers' buffers in earlier kernels of this stream are visible before the flag),
+// then waits until every rank's flag in ITS OWN array has reached the epoch (acquire).  One warp; bounded spin (a rank that
+// never arrives traps the kernel instead of hanging the GPU).
+__global__ void peer_barrier_kernel(GatherOut flags, int rank, uint32_t epoch) {
+    const int t = threadIdx.x;
+    if (t < flags.world) {
+        __threadfence_system();
+        uint32_t *theirs = reinterpret_cast<uint32_t *>(flags.peer[t]) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(flags.peer[rank]) + t;
+        uint32_t v = 0;
+        for (long long spin = 0; spin < (1ll << 31); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+        }
+        if ((int32_t)(v - epoch) < 0) __trap();
+    }
+}
+
+__global__ void fill_bytes_kernel(GatherOut G, long long begin, long long count, unsigned char value) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count * G.world; i += (long long)gridDim.x * blockDim.x)
+        G.peer[i / count][G.offset + begin + i % count] = value;
+}
+
+// int32 labels -> bytes written into slot [rank] of every rank's gathered buffer (the models without a fused store)
+__global__ void scatter_labels_kernel(GatherOut G, const int32_t *__restrict__ labels, long long n) {
+    const long long n16 = (n + 15) / 16;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n16; c += (long long)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const long long e = c * 16 + k;
+            if (e < n) w[k >> 2] = (w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (((uint32_t)labels[e] & 0xFFu) << (8 * (k & 3)));
+        }
+        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int pr = 0; pr < G.world; ++pr) *reinterpret_cast<uint4 *>(G.peer[pr] + G.offset + c * 16) = v;
     }
 }
 
@@ -214,8 +261,119 @@ int tcsdn_allgather_labels_u8(tcsdn_comm_t *c, const int32_t *local, int64_t n_l
     return TCSDN_OK;
 }
 
+/* ---- peer-memory exchange: the gathered label vector is written by the classification kernels themselves --------------- */
+
+static void gather_release(tcsdn_comm *c) {
+    for (int r = 0; r < c->world && r < kMaxPeers; ++r) {
+        if (!c->g_peer[r]) continue;
+        if (r == c->rank) cudaFree(c->g_peer[r]); else cudaIpcCloseMemHandle(c->g_peer[r]);
+        c->g_peer[r] = nullptr;
+    }
+    c->g_block = c->g_bytes = 0;
+}
+
+int tcsdn_comm_gather_buffer(tcsdn_comm_t *c, int64_t n_block, const uint8_t **gathered_out, int64_t *slot_bytes_out) {
+    if (!c || n_block < 0) { set_error("comm_gather_buffer: bad arguments"); return TCSDN_EINVAL; }
+    if (c->world > kMaxPeers) { set_error("comm_gather_buffer: at most %d ranks (one NVSwitch domain)", kMaxPeers); return TCSDN_EINVAL; }
+    const int64_t blk = (n_block + 15) & ~(int64_t)15;
+    if (c->g_block < blk) {   // collective (re)allocation: every rank calls with the same n_block
+        cudaDeviceSynchronize();
+        gather_release(c);
+        const size_t label_bytes = (size_t)blk * c->world;
+        const size_t total = 2 * label_bytes + 256;                     // two epochs, then world flag words (zeroed)
+        uint8_t *mine = nullptr;
+        TCSDN_CUDA(cudaMalloc(&mine, total));
+        TCSDN_CUDA(cudaMemset(mine, 0xFF, 2 * label_bytes));
+        TCSDN_CUDA(cudaMemset(mine + 2 * label_bytes, 0, 256));
+        c->g_peer[c->rank] = mine;
+        c->g_block = blk; c->g_bytes = (int64_t)label_bytes; c->g_epoch = 0;
+        if (c->world > 1) {
+            // exchange the CUDA IPC handles through the communicator itself (64 bytes per rank)
+            cudaIpcMemHandle_t h;
+            TCSDN_CUDA(cudaIpcGetMemHandle(&h, mine));
+            uint8_t *d_h = nullptr;
+            TCSDN_CUDA(cudaMalloc(&d_h, sizeof(h) * (size_t)(c->world + 1)));
+            TCSDN_CUDA(cudaMemcpy(d_h, &h, sizeof(h), cudaMemcpyHostToDevice));
+            ncclResult_t nr = g_nccl.AllGather(d_h, d_h + sizeof(h), sizeof(h), ncclUint8, c->comm, nullptr);
+            if (nr != ncclSuccess) { cudaFree(d_h); set_error("ncclAllGather(ipc handles) failed: %s", g_nccl.GetErrorString(nr)); return TCSDN_ECUDA; }
+            std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+            cudaError_t e = cudaMemcpy(all.data(), d_h + sizeof(h), sizeof(h) * (size_t)c->world, cudaMemcpyDeviceToHost);   // synchronises
+            cudaFree(d_h);
+            if (e != cudaSuccess) { set_error("ipc handle exchange failed: %s", cudaGetErrorString(e)); return TCSDN_ECUDA; }
+            for (int r = 0; r < c->world; ++r) {
+                if (r == c->rank) continue;
+                void *p = nullptr;
+                e = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); return TCSDN_ECUDA; }
+                c->g_peer[r] = static_cast<uint8_t *>(p);
+            }
+        }
+    }
+    if (gathered_out) *gathered_out = c->g_peer[c->rank];
+    if (slot_bytes_out) *slot_bytes_out = c->g_block;
+    return TCSDN_OK;
+}
+
+int tcsdn_predict_gathered(tcsdn_model_t *m, tcsdn_comm_t *c, const void *x, int64_t n_local, int32_t d, int32_t x_dtype,
+                           const uint8_t **gathered_out, void *cuda_stream) {
+    if (!m || !c || n_local < 0 || (n_local > 0 && !x)) { set_error("predict_gathered: bad arguments"); return TCSDN_EINVAL; }
+    if (d != m->d) { set_error("X has %d features, but the model is expecting %d features as input", d, m->d); return TCSDN_EINVAL; }
+    if (x_dtype != TCSDN_F32 && x_dtype != TCSDN_F64) { set_error("x_dtype must be TCSDN_F32 or TCSDN_F64"); return TCSDN_EINVAL; }
+    if (m->n_classes > 255 && m->kind != TCSDN_KIND_FOREST && m->kind != TCSDN_KIND_KNN && m->kind != TCSDN_KIND_SVC) {
+        set_error("predict_gathered: labels travel as bytes, the model has %d classes", m->n_classes); return TCSDN_EINVAL; }
+    if (!c->g_peer[c->rank] || n_local > c->g_block) { set_error("predict_gathered: call tcsdn_comm_gather_buffer(n_block >= %lld) first", (long long)n_local); return TCSDN_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint32_t epoch = ++c->g_epoch;
+    GatherOut G, F;
+    memset(&G, 0, sizeof(G)); memset(&F, 0, sizeof(F));
+    G.world = F.world = c->world;
+    G.offset = (long long)c->rank * c->g_block;
+    for (int r = 0; r < c->world; ++r) {
+        G.peer[r] = c->g_peer[r] + (size_t)(epoch & 1) * (size_t)c->g_bytes;   // two label buffers alternate (see below)
+        F.peer[r] = c->g_peer[r] + 2 * (size_t)c->g_bytes;                     // the flag words
+    }
+    int rc = TCSDN_OK;
+    const bool fused = (m->kind == TCSDN_KIND_LINEAR || m->kind == TCSDN_KIND_GNB || m->kind == TCSDN_KIND_KMEANS) && m->sp_valid &&
+                       (m->d == 4 || m->d == 8 || m->d == 12 || m->d == 16) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && m->opt_engine != 1;
+    if (n_local > 0) {
+        if (fused) {
+            // ONE kernel classifies the block and stores every label into all ranks' buffers (scorers.cu store_labels)
+            rc = launch_scorer(m, x, n_local, x_dtype, nullptr, nullptr, m->opt_check_finite ? m->d_flag : nullptr, st, &G);
+        } else {
+            // the other estimators: their own kernels into a local int32 vector, then one scatter kernel over peer memory
+            if (c->pad_cap < n_local) {
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(st, &cap);
+                if (cap != cudaStreamCaptureStatusNone) { set_error("predict_gathered: first call allocates; make it outside the graph capture"); return TCSDN_EINVAL; }
+                if (c->d_pad) cudaFree(c->d_pad);
+                c->d_pad = nullptr; c->pad_cap = 0;
+                TCSDN_CUDA(cudaMalloc(&c->d_pad, (size_t)c->g_block * sizeof(int32_t)));
+                c->pad_cap = c->g_block;
+            }
+            rc = tcsdn_predict(m, x, n_local, d, x_dtype, TCSDN_DEVICE, c->d_pad, nullptr, cuda_stream);
+            if (rc == TCSDN_OK) {
+                int64_t blocks = ((n_local + 15) / 16 + 255) / 256;
+                if (blocks > 148 * 4) blocks = 148 * 4;
+                scatter_labels_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, c->d_pad, n_local);
+            }
+        }
+        if (rc != TCSDN_OK) return rc;
+    }
+    const int64_t done16 = (n_local + 15) & ~(int64_t)15;
+    if (done16 < c->g_block)   // a short block: the rest of the slot reads -1 (0xFF) on every rank
+        fill_bytes_kernel<<<8, 256, 0, st>>>(G, done16, c->g_block - done16, 0xFF);
+    // Everybody's bytes have landed when the barrier kernel retires.  Two label buffers alternate by epoch: a rank can only
+    // start writing epoch e + 2 into a peer after that peer has entered the barrier of epoch e + 1, i.e. after everything the
+    // peer enqueued behind barrier e -- its readers of buffer e -- has run.
+    peer_barrier_kernel<<<1, 32, 0, st>>>(F, c->rank, epoch);
+    TCSDN_CUDA(cudaGetLastError());
+    if (gathered_out) *gathered_out = G.peer[c->rank];
+    return TCSDN_OK;
+}
+
 void tcsdn_comm_destroy(tcsdn_comm_t *c) {
     if (!c) return;
+    gather_release(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->d_pad) cudaFree(c->d_pad);
     if (c->d_bytes) cudaFree(c->d_bytes);

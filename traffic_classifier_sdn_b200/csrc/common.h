@@ -52,6 +52,15 @@ struct ScorerParams {
     float kf[kMaxClassesFast];
 };
 
+// Peer-memory label exchange (comm.cu): where a classification kernel writes its labels, one byte each, when the caller wants
+// the gathered vector on every rank -- slot [rank] of EVERY rank's buffer (own + peers over NVLink).  world == 0: not gathering.
+constexpr int kMaxPeers = 8;
+struct GatherOut {
+    unsigned char *peer[kMaxPeers];   // this epoch's gathered buffer of every rank (device pointers, peers opened through CUDA IPC)
+    long long offset;                 // rank * n_block (a multiple of 16)
+    int world;
+};
+
 struct DeviceBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -132,7 +141,7 @@ namespace tcsdn {
 // kernels' host launchers (each enqueues on `st`, returns TCSDN_*).  x is a DEVICE pointer.
 // `flag` (nullable): device int32 the kernels OR 1 into when a row holds NaN/inf.
 int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  int32_t *flag, cudaStream_t st);
+                  int32_t *flag, cudaStream_t st, const GatherOut *gather = nullptr);
 int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
                   int32_t *flag, cudaStream_t st);
 int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,

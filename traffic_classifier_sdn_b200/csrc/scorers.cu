@@ -182,9 +182,11 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
                                                                 const T *__restrict__ X, int64_t n,
                                                                 int32_t *__restrict__ labels,
                                                                 double *__restrict__ scores, int32_t *flag,
-                                                                unsigned long long *refined) {
+                                                                unsigned long long *refined,
+                                                                const __grid_constant__ GatherOut G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kTile = kThreads * kRPT;
+    __shared__ __align__(16) unsigned char slab[kTile];   // gathered mode: the tile's labels as bytes
     constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
     T *tiles = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTileBytes);
@@ -200,6 +202,28 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // Labels of one tile.  Plain mode: int32 per row.  Gathered mode (G.world > 0): one byte per row, staged in shared memory
+    // and written with 16-byte stores into slot [rank] of every rank's gathered buffer -- the all-gather of the label vectors
+    // happens HERE, tile by tile over NVLink peer memory, under the streaming of the next rows (comm.cu: tcsdn_predict_gathered).
+    auto store_labels = [&](int64_t row0, const int (&arg)[kRPT]) {
+#pragma unroll
+        for (int q = 0; q < kRPT; ++q) {
+            const int64_t row = row0 + q * kThreads + tid;
+            if (labels && row < n) labels[row] = arg[q];
+            if (G.world) slab[q * kThreads + tid] = row < n ? (unsigned char)arg[q] : (unsigned char)0xFF;
+        }
+        if (G.world) {
+            __syncthreads();
+            constexpr int kChunks = kTile / 16;
+            for (int e = tid; e < kChunks * G.world; e += kThreads) {
+                const int pr = e / kChunks, ch = e - pr * kChunks;
+                if (row0 + ch * 16 < n)
+                    *reinterpret_cast<uint4 *>(G.peer[pr] + G.offset + row0 + ch * 16) = *reinterpret_cast<const uint4 *>(slab + ch * 16);
+            }
+            __syncthreads();
+        }
+    };
 
     auto issue = [&](int64_t tile, int stage) {
         int64_t row0 = tile * kTile;
@@ -261,9 +285,8 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
                         arg[q] = a1[0];
                         ++redo;
                     }
-                    const int64_t row = row0 + q * kThreads + tid;
-                    if (row < n) labels[row] = arg[q];
                 }
+                store_labels(row0, arg);
                 if (redo) atomicAdd(refined, (unsigned long long)redo);
                 continue;
             }
@@ -292,14 +315,12 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {
             const int64_t row = row0 + q * kThreads + tid;
-            if (row < n) {
-                labels[row] = arg[q];
-                if (scores) {
+            if (row < n && scores) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) scores[row * R + r] = s[q][r];
-                }
+                for (int r = 0; r < R; ++r) scores[row * R + r] = s[q][r];
             }
         }
+        store_labels(row0, arg);
     }
     if (flag && nf != nf) atomicOr(flag, 1);
 }
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(256) scorer_generic_kernel(const T *__restrict
 
 template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
 static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
-                            cudaStream_t st, int ctas_per_sm) {
+                            cudaStream_t st, int ctas_per_sm, const GatherOut &G) {
     constexpr int kTile = kThreads * kRPT;
     auto kern = scorer_tiled_kernel<T, D, R, KIND, kThreads, kRPT>;
     const size_t smem = (size_t)kStages * kTile * D * sizeof(T) + kStages * sizeof(uint64_t);
@@ -358,37 +379,38 @@ static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labe
     // sit on the SMs waiting.  Plain launches it is.)
     // fp32 pre-pass: GaussianNB, float32 rows, labels only (TCSDN_OPT_ENGINE = 1 routes to the generic fp64 kernel instead)
     unsigned long long *refined = (KIND == KIND_GNB && sizeof(T) == 4 && scores == nullptr) ? m->d_refined : nullptr;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag, refined);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(m->sp, x, n, labels, scores, flag, refined, G);
     TCSDN_CUDA(cudaGetLastError());
     return TCSDN_OK;
 }
 
 template <typename T, int D, int R, int KIND>
 static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
-                        cudaStream_t st) {
+                        cudaStream_t st, const GatherOut &G) {
     // CTA shape (measured on B200, 1M x 8 GaussianNB / 10M x 12 LogisticRegression, rows/s):
     //   128 threads x 4 rows: 8.3e10 / 1.105e11    256 x 2: 7.9e10 / 1.132e11    256 x 4: 7.7e10 / 9.7e10    128 x 8: 8.3e10 / 7.7e10
     // GaussianNB (fp64-pipe-bound) wants the constants amortised over 4 rows, the HBM-bound max/min scorers want more warps.
     // Small batches: with 512-row tiles a 1M-row batch is 4.4 tiles per CTA -- the pipeline ramp (first tile) and the tail
     // (some CTAs own one tile more) are a quarter of the step -- so below 16 tiles per CTA the 256-row shape (128 x 2) is used.
-    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 / 3 forces 128 x 4 / 256 x 2 / 128 x 2.
+    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 / 3 / 4 forces 128 x 4 / 256 x 2 / 128 x 2 / 128 x 1.
     const int per_sm = sizeof(T) == 4 ? 3 : 2;
     int shape = (int)m->opt_scorer_shape;
     if (shape == 0) {
         shape = KIND != KIND_GNB ? 2 : 1;
         if ((n + 511) / 512 < (int64_t)16 * m->sm_count * per_sm) shape = 3;
     }
-    if (shape == 2) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm);
-    if (shape == 3) return launch_tiled_cfg<T, D, R, KIND, 128, 2>(m, x, n, labels, scores, flag, st, per_sm + 1);
-    return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm);
+    if (shape == 2) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm, G);
+    if (shape == 3) return launch_tiled_cfg<T, D, R, KIND, 128, 2>(m, x, n, labels, scores, flag, st, per_sm + 1, G);
+    if (shape == 4) return launch_tiled_cfg<T, D, R, KIND, 128, 1>(m, x, n, labels, scores, flag, st, 2 * per_sm + 2, G);
+    return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm, G);
 }
 
 template <typename T, int D, int KIND>
 static int dispatch_rows(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
-                         cudaStream_t st) {
+                         cudaStream_t st, const GatherOut &G) {
     switch (m->n_classes) {
 #define TCSDN_CASE(RR) \
-    case RR: return launch_tiled<T, D, RR, KIND>(m, x, n, labels, scores, flag, st);
+    case RR: return launch_tiled<T, D, RR, KIND>(m, x, n, labels, scores, flag, st, G);
         TCSDN_CASE(1) TCSDN_CASE(2) TCSDN_CASE(3) TCSDN_CASE(4) TCSDN_CASE(5) TCSDN_CASE(6) TCSDN_CASE(7)
         TCSDN_CASE(8)
 #undef TCSDN_CASE
@@ -398,22 +420,23 @@ static int dispatch_rows(tcsdn_model *m, const T *x, int64_t n, int32_t *labels,
 
 template <typename T, int D>
 static int dispatch_kind(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
-                         int32_t *flag, cudaStream_t st) {
-    if (kind == KIND_GNB) return dispatch_rows<T, D, KIND_GNB>(m, x, n, labels, scores, flag, st);
-    if (kind == KIND_AFFINE_MIN) return dispatch_rows<T, D, KIND_AFFINE_MIN>(m, x, n, labels, scores, flag, st);
-    return dispatch_rows<T, D, KIND_AFFINE_MAX>(m, x, n, labels, scores, flag, st);
+                         int32_t *flag, cudaStream_t st, const GatherOut &G) {
+    if (kind == KIND_GNB) return dispatch_rows<T, D, KIND_GNB>(m, x, n, labels, scores, flag, st, G);
+    if (kind == KIND_AFFINE_MIN) return dispatch_rows<T, D, KIND_AFFINE_MIN>(m, x, n, labels, scores, flag, st, G);
+    return dispatch_rows<T, D, KIND_AFFINE_MAX>(m, x, n, labels, scores, flag, st, G);
 }
 
 template <typename T>
 static int launch_scorer_t(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
-                           int32_t *flag, cudaStream_t st) {
+                           int32_t *flag, cudaStream_t st, const GatherOut &G) {
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (m->sp_valid && aligned && m->opt_engine != 1) {
-        if (m->d == 12) return dispatch_kind<T, 12>(m, kind, x, n, labels, scores, flag, st);
-        if (m->d == 8) return dispatch_kind<T, 8>(m, kind, x, n, labels, scores, flag, st);
-        if (m->d == 16) return dispatch_kind<T, 16>(m, kind, x, n, labels, scores, flag, st);
-        if (m->d == 4) return dispatch_kind<T, 4>(m, kind, x, n, labels, scores, flag, st);
+        if (m->d == 12) return dispatch_kind<T, 12>(m, kind, x, n, labels, scores, flag, st, G);
+        if (m->d == 8) return dispatch_kind<T, 8>(m, kind, x, n, labels, scores, flag, st, G);
+        if (m->d == 16) return dispatch_kind<T, 16>(m, kind, x, n, labels, scores, flag, st, G);
+        if (m->d == 4) return dispatch_kind<T, 4>(m, kind, x, n, labels, scores, flag, st, G);
     }
+    if (G.world) { set_error("fused gather needs the tiled scorer (d in {4, 8, 12, 16}, <= 8 score rows, 16-byte aligned rows)"); return TCSDN_EINVAL; }
     int64_t blocks = (n + 255) / 256;
     int64_t cap = (int64_t)m->sm_count * 8;
     if (blocks > cap) blocks = cap;
@@ -424,12 +447,15 @@ static int launch_scorer_t(tcsdn_model *m, int kind, const T *x, int64_t n, int3
 }
 
 int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
-                  int32_t *flag, cudaStream_t st) {
+                  int32_t *flag, cudaStream_t st, const GatherOut *gather) {
     if (n == 0) return TCSDN_OK;
+    GatherOut G;
+    memset(&G, 0, sizeof(G));
+    if (gather) G = *gather;
     int kind = m->kind == TCSDN_KIND_GNB ? KIND_GNB : (m->kind == TCSDN_KIND_KMEANS ? KIND_AFFINE_MIN : KIND_AFFINE_MAX);
     m->stats[0] += 1;
-    if (dtype == TCSDN_F32) return launch_scorer_t<float>(m, kind, static_cast<const float *>(x), n, labels, scores, flag, st);
-    return launch_scorer_t<double>(m, kind, static_cast<const double *>(x), n, labels, scores, flag, st);
+    if (dtype == TCSDN_F32) return launch_scorer_t<float>(m, kind, static_cast<const float *>(x), n, labels, scores, flag, st, G);
+    return launch_scorer_t<double>(m, kind, static_cast<const double *>(x), n, labels, scores, flag, st, G);
 }
 
 }  // namespace tcsdn

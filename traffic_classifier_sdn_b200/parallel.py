@@ -61,6 +61,34 @@ class Communicator:
                                                         C.c_void_p(st)))
         return out
 
+    # ---- the exchange fused into the classification (include/tcsdn.h: tcsdn_comm_gather_buffer / tcsdn_predict_gathered)
+    def gather_buffer(self, n_block: int) -> int:
+        """Collective: size the peer-memory label buffers for blocks of up to n_block rows.  -> bytes per rank slot."""
+        ptr, slot = C.c_void_p(), C.c_int64(0)
+        _lib.check(self._lib.tcsdn_comm_gather_buffer(self._h, int(n_block), C.byref(ptr), C.byref(slot)))
+        self._slot = int(slot.value)
+        return self._slot
+
+    def predict_gathered(self, model, X):
+        """Classify this rank's block X (CUDA tensor [n_local, d]) with the labels of ALL ranks as the result: a CUDA uint8
+        tensor [world, slot_bytes] (255 = padding) that aliases the library's buffer -- valid until the call after the next.
+        Every rank calls it; LogisticRegression / GaussianNB / KMeans store into the peers from inside their kernel.
+        Blocks of different lengths (a short last shard): call ``gather_buffer(n_block)`` with the common block size first."""
+        import torch
+        model._check_fitted()
+        if not getattr(self, "_slot", 0) or X.shape[0] > self._slot:
+            self.gather_buffer(X.shape[0])
+        X = X.contiguous()
+        out = C.c_void_p()
+        with torch.cuda.device(X.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._lib.tcsdn_predict_gathered(model._handle, self._h, C.c_void_p(X.data_ptr()), X.shape[0], X.shape[1],
+                                                        _lib.F32 if X.dtype == torch.float32 else _lib.F64, C.byref(out), C.c_void_p(st)))
+
+        class _View:   # zero-copy view of the library's device buffer
+            __cuda_array_interface__ = {"shape": (self.world, self._slot), "typestr": "|u1", "data": (int(out.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=X.device)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.tcsdn_comm_destroy(self._h)
