@@ -189,8 +189,9 @@ int tcsdn_allgather_labels_u8(tcsdn_comm_t *comm, const int32_t *local, int64_t 
  * next rows stream in, and a peer-memory barrier closes the call: when `cuda_stream` reaches its end, *gathered_out
  * (device, [world][slot_bytes], 0xFF = -1 padding) holds every rank's labels.  LogisticRegression / GaussianNB / KMeans
  * store from inside their scoring kernel; the other estimators run their kernels and one scatter kernel.  No NCCL call, no
- * host synchronisation: capturable into a CUDA graph.  Two label buffers alternate between calls, so the vector of call k
- * stays valid until call k + 2 is enqueued.
+ * host synchronisation: capturable into a CUDA graph (the barriers' generation counters live in device memory).  A
+ * barrier at the START of the call keeps any rank from overwriting the previous vector before every rank has reached its
+ * next call, so what a rank enqueues between two calls reads a consistent vector at a stable address.
  *   tcsdn_comm_gather_buffer  collective; sizes (or grows) the buffers for blocks of up to n_block rows, exchanges the IPC
  *                             handles through the communicator; slot_bytes_out = n_block rounded up to 16
  *   tcsdn_predict_gathered    x [n_local][d] on the device, n_local <= slot_bytes; every rank of the communicator calls it */

@@ -93,8 +93,7 @@ def test_comm_world1_allgather_u8_wire(n_local, n_block, n_classes):
 @pytest.mark.parametrize("kind", ["gnb", "linear", "forest", "knn"])
 def test_predict_gathered_world1(kind, specs):
     """tcsdn_predict_gathered on one rank: the fused store path of the scorers and the scatter path of the other estimators
-    fill slot 0 of the peer-memory buffer with the labels as bytes (255 padding), also inside a CUDA graph and across the
-    two alternating label buffers"""
+    fill slot 0 of the peer-memory buffer with the labels as bytes (255 padding), also inside a CUDA graph replayed twice"""
     import torch
     import torch.distributed as dist
     from traffic_classifier_sdn_b200 import from_spec, synth
@@ -108,7 +107,7 @@ def test_predict_gathered_world1(kind, specs):
         for n in (5003, 1000):
             X = torch.from_numpy(synth.make_flows(n, seed=n, return_labels=False).astype(np.float32)).cuda()
             ref = est.predict_indices(X).cpu().numpy()
-            for rep in range(3):                           # epochs 1, 2, 3: both label buffers
+            for rep in range(3):                           # several generations of both barriers
                 got = comm.predict_gathered(est, X)
                 torch.cuda.synchronize()
                 g = got.cpu().numpy()
@@ -119,10 +118,11 @@ def test_predict_gathered_world1(kind, specs):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             got = comm.predict_gathered(est, X)
-        got.zero_()
-        graph.replay()
-        torch.cuda.synchronize()
-        assert np.array_equal(got.cpu().numpy()[0, :n], ref.astype(np.uint8))
+        for _ in range(2):
+            got.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy()[0, :n], ref.astype(np.uint8))
     finally:
         comm.close()
 

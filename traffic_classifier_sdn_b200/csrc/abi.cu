@@ -373,7 +373,7 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
             m->opt_chunk_rows = value; return TCSDN_OK;
         case TCSDN_OPT_CHECK_FINITE: m->opt_check_finite = value ? 1 : 0; return TCSDN_OK;
         case TCSDN_OPT_SCORER_SHAPE:
-            if (value < 0 || value > 4) { set_error("scorer shape must be 0..4"); return TCSDN_EINVAL; }
+            if (value < 0 || value > 3) { set_error("scorer shape must be 0..3"); return TCSDN_EINVAL; }
             m->opt_scorer_shape = value; return TCSDN_OK;
         case TCSDN_OPT_FOREST_SHAPE:
             if (value < 0 || value > 3) { set_error("forest shape must be 0..3"); return TCSDN_EINVAL; }

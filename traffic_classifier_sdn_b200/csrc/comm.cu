@@ -68,12 +68,11 @@ struct tcsdn_comm {
     int64_t pad_cap = 0;
     uint8_t *d_bytes = nullptr; // byte-wide wire format: [n_block] packed local labels, then [world * n_block] gathered
     int64_t bytes_cap = 0;      // in units of n_block
-    // peer-memory exchange (tcsdn_comm_gather_buffer): one allocation per rank = 2 epochs x [world][g_block] label bytes,
-    // then the barrier flags; g_peer[r] = rank r's allocation as seen from this process (CUDA IPC; [rank] = the local one)
+    // peer-memory exchange (tcsdn_comm_gather_buffer): one allocation per rank = [world][g_block] label bytes, then 256 bytes
+    // of barrier flags; g_peer[r] = rank r's allocation as seen from this process (CUDA IPC; [rank] = the local one)
     uint8_t *g_peer[tcsdn::kMaxPeers] = {nullptr};
     int64_t g_block = 0;        // bytes per rank slot (multiple of 16)
-    int64_t g_bytes = 0;        // label bytes per epoch = world * g_block
-    uint32_t g_epoch = 0;       // calls so far (flags carry it)
+    int64_t g_bytes = 0;        // label bytes = world * g_block
 };
 
 namespace tcsdn {
@@ -111,23 +110,23 @@ __global__ void labels_unpack_u8(const uint8_t *__restrict__ src, int32_t *__res
     }
 }
 
-// Cross-rank barrier over peer memory: rank writes its epoch into slot [rank] of every rank's flag array (release, system
-// scope: the label bytes this rank stored into the peers' buffers in earlier kernels of this stream are visible before the flag),
-// then waits until every rank's flag in ITS OWN array has reached the epoch (acquire).  One warp; bounded spin (a rank that
-// never arrives traps the kernel instead of hanging the GPU).
-__global__ void peer_barrier_kernel(GatherOut flags, int rank, uint32_t epoch) {
-    const int t = threadIdx.x;
-    if (t < flags.world) {
+// Cross-rank barrier over peer memory.  Every rank keeps, at the end of its buffer, two flag arrays (barrier A = "I have
+// entered the call", barrier B = "my label bytes are out") and a generation counter per barrier -- in DEVICE memory, so that a
+// CUDA graph holding these kernels can be replayed (a generation passed as a kernel argument would be frozen at capture).
+// The warp bumps the generation, writes it into slot [rank] of every rank's flag array (release, system scope: the label
+// bytes this rank stored into the peers' buffers in earlier kernels of the stream are visible before the flag) and waits
+// until every rank's flag in ITS OWN array has reached it (acquire).  Bounded spin: a rank that never arrives traps the
+// kernel instead of hanging the GPU.
+__global__ void peer_barrier_kernel(GatherOut G, int which) {
+    // generations: A at +32, B at +33; ONE A and ONE B per call, both advanced by the call's B barrier (barrier A may be fused
+    // into the scoring kernel, which only reads its generation)
+    unsigned *ctl = G.flags[G.rank];
+    const unsigned epoch = ctl[32 + which] + 1;
+    if (threadIdx.x == 0) {
         __threadfence_system();
-        uint32_t *theirs = reinterpret_cast<uint32_t *>(flags.peer[t]) + rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
-        const uint32_t *mine = reinterpret_cast<const uint32_t *>(flags.peer[rank]) + t;
-        uint32_t v = 0;
-        for (long long spin = 0; spin < (1ll << 31); ++spin) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if ((int32_t)(v - epoch) >= 0) break;
-        }
-        if ((int32_t)(v - epoch) < 0) __trap();
+        peer_flag_arrive(G, which, epoch);
+        peer_flag_wait(G, which, epoch);
+        if (which == 1) { ctl[33] = epoch; ctl[32] = ctl[32] + 1; }
     }
 }
 
@@ -280,13 +279,13 @@ int tcsdn_comm_gather_buffer(tcsdn_comm_t *c, int64_t n_block, const uint8_t **g
         cudaDeviceSynchronize();
         gather_release(c);
         const size_t label_bytes = (size_t)blk * c->world;
-        const size_t total = 2 * label_bytes + 256;                     // two epochs, then world flag words (zeroed)
+        const size_t total = label_bytes + 256;                         // labels, then the barrier flags (zeroed)
         uint8_t *mine = nullptr;
         TCSDN_CUDA(cudaMalloc(&mine, total));
-        TCSDN_CUDA(cudaMemset(mine, 0xFF, 2 * label_bytes));
-        TCSDN_CUDA(cudaMemset(mine + 2 * label_bytes, 0, 256));
+        TCSDN_CUDA(cudaMemset(mine, 0xFF, label_bytes));
+        TCSDN_CUDA(cudaMemset(mine + label_bytes, 0, 256));
         c->g_peer[c->rank] = mine;
-        c->g_block = blk; c->g_bytes = (int64_t)label_bytes; c->g_epoch = 0;
+        c->g_block = blk; c->g_bytes = (int64_t)label_bytes;
         if (c->world > 1) {
             // exchange the CUDA IPC handles through the communicator itself (64 bytes per rank)
             cudaIpcMemHandle_t h;
@@ -323,51 +322,56 @@ int tcsdn_predict_gathered(tcsdn_model_t *m, tcsdn_comm_t *c, const void *x, int
         set_error("predict_gathered: labels travel as bytes, the model has %d classes", m->n_classes); return TCSDN_EINVAL; }
     if (!c->g_peer[c->rank] || n_local > c->g_block) { set_error("predict_gathered: call tcsdn_comm_gather_buffer(n_block >= %lld) first", (long long)n_local); return TCSDN_EINVAL; }
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    const uint32_t epoch = ++c->g_epoch;
-    GatherOut G, F;
-    memset(&G, 0, sizeof(G)); memset(&F, 0, sizeof(F));
-    G.world = F.world = c->world;
+    GatherOut G;
+    memset(&G, 0, sizeof(G));
+    G.world = c->world; G.rank = c->rank;
+    G.slot = c->g_block;
     G.offset = (long long)c->rank * c->g_block;
     for (int r = 0; r < c->world; ++r) {
-        G.peer[r] = c->g_peer[r] + (size_t)(epoch & 1) * (size_t)c->g_bytes;   // two label buffers alternate (see below)
-        F.peer[r] = c->g_peer[r] + 2 * (size_t)c->g_bytes;                     // the flag words
+        G.peer[r] = c->g_peer[r];
+        G.flags[r] = reinterpret_cast<unsigned *>(c->g_peer[r] + (size_t)c->g_bytes);   // the barrier words behind the labels
     }
-    int rc = TCSDN_OK;
-    const bool fused = (m->kind == TCSDN_KIND_LINEAR || m->kind == TCSDN_KIND_GNB || m->kind == TCSDN_KIND_KMEANS) && m->sp_valid &&
-                       (m->d == 4 || m->d == 8 || m->d == 12 || m->d == 16) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && m->opt_engine != 1;
+    const bool fused = n_local > 0 && (m->kind == TCSDN_KIND_LINEAR || m->kind == TCSDN_KIND_GNB || m->kind == TCSDN_KIND_KMEANS) &&
+                       x_dtype == TCSDN_F32 && m->sp_valid && (m->d == 4 || m->d == 8 || m->d == 12 || m->d == 16) &&
+                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && m->opt_engine != 1;
+    if (fused) {
+        // ONE kernel classifies and gathers: it arrives at barrier A when it starts, every CTA waits for A before its first store
+        // into the peers, and stores each label byte into all ranks' buffers (scorers.cu); then the one-warp barrier B
+        TCSDN_TRY(launch_scorer(m, x, n_local, x_dtype, nullptr, nullptr, m->opt_check_finite ? m->d_flag : nullptr, st, &G));
+        const int64_t d16 = (n_local + 15) & ~(int64_t)15;
+        if (d16 < c->g_block) fill_bytes_kernel<<<8, 256, 0, st>>>(G, d16, c->g_block - d16, 0xFF);
+        peer_barrier_kernel<<<1, 32, 0, st>>>(G, 1);
+        TCSDN_CUDA(cudaGetLastError());
+        if (gathered_out) *gathered_out = c->g_peer[c->rank];
+        return TCSDN_OK;
+    }
+    // The other estimators: their own kernels into a local int32 vector first (no peer is touched), then barrier A -- no rank
+    // stores a label of this call before every rank has ENTERED the call, i.e. before everything the others enqueued behind
+    // their previous call (the readers of the previous vector) has run --, one scatter kernel over peer memory, barrier B.
     if (n_local > 0) {
-        if (fused) {
-            // ONE kernel classifies the block and stores every label into all ranks' buffers (scorers.cu store_labels)
-            rc = launch_scorer(m, x, n_local, x_dtype, nullptr, nullptr, m->opt_check_finite ? m->d_flag : nullptr, st, &G);
-        } else {
-            // the other estimators: their own kernels into a local int32 vector, then one scatter kernel over peer memory
-            if (c->pad_cap < n_local) {
-                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-                cudaStreamIsCapturing(st, &cap);
-                if (cap != cudaStreamCaptureStatusNone) { set_error("predict_gathered: first call allocates; make it outside the graph capture"); return TCSDN_EINVAL; }
-                if (c->d_pad) cudaFree(c->d_pad);
-                c->d_pad = nullptr; c->pad_cap = 0;
-                TCSDN_CUDA(cudaMalloc(&c->d_pad, (size_t)c->g_block * sizeof(int32_t)));
-                c->pad_cap = c->g_block;
-            }
-            rc = tcsdn_predict(m, x, n_local, d, x_dtype, TCSDN_DEVICE, c->d_pad, nullptr, cuda_stream);
-            if (rc == TCSDN_OK) {
-                int64_t blocks = ((n_local + 15) / 16 + 255) / 256;
-                if (blocks > 148 * 4) blocks = 148 * 4;
-                scatter_labels_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, c->d_pad, n_local);
-            }
+        if (c->pad_cap < n_local) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cap);
+            if (cap != cudaStreamCaptureStatusNone) { set_error("predict_gathered: first call allocates; make it outside the graph capture"); return TCSDN_EINVAL; }
+            if (c->d_pad) cudaFree(c->d_pad);
+            c->d_pad = nullptr; c->pad_cap = 0;
+            TCSDN_CUDA(cudaMalloc(&c->d_pad, (size_t)c->g_block * sizeof(int32_t)));
+            c->pad_cap = c->g_block;
         }
-        if (rc != TCSDN_OK) return rc;
+        TCSDN_TRY(tcsdn_predict(m, x, n_local, d, x_dtype, TCSDN_DEVICE, c->d_pad, nullptr, cuda_stream));
+    }
+    peer_barrier_kernel<<<1, 32, 0, st>>>(G, 0);
+    if (n_local > 0) {
+        int64_t blocks = ((n_local + 15) / 16 + 255) / 256;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        scatter_labels_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, c->d_pad, n_local);
     }
     const int64_t done16 = (n_local + 15) & ~(int64_t)15;
     if (done16 < c->g_block)   // a short block: the rest of the slot reads -1 (0xFF) on every rank
         fill_bytes_kernel<<<8, 256, 0, st>>>(G, done16, c->g_block - done16, 0xFF);
-    // Everybody's bytes have landed when the barrier kernel retires.  Two label buffers alternate by epoch: a rank can only
-    // start writing epoch e + 2 into a peer after that peer has entered the barrier of epoch e + 1, i.e. after everything the
-    // peer enqueued behind barrier e -- its readers of buffer e -- has run.
-    peer_barrier_kernel<<<1, 32, 0, st>>>(F, c->rank, epoch);
+    peer_barrier_kernel<<<1, 32, 0, st>>>(G, 1);   // everybody's bytes have landed when it retires
     TCSDN_CUDA(cudaGetLastError());
-    if (gathered_out) *gathered_out = G.peer[c->rank];
+    if (gathered_out) *gathered_out = c->g_peer[c->rank];
     return TCSDN_OK;
 }
 

@@ -56,10 +56,31 @@ struct ScorerParams {
 // the gathered vector on every rank -- slot [rank] of EVERY rank's buffer (own + peers over NVLink).  world == 0: not gathering.
 constexpr int kMaxPeers = 8;
 struct GatherOut {
-    unsigned char *peer[kMaxPeers];   // this epoch's gathered buffer of every rank (device pointers, peers opened through CUDA IPC)
-    long long offset;                 // rank * n_block (a multiple of 16)
-    int world;
+    unsigned char *peer[kMaxPeers];   // the gathered buffer of every rank (device pointers, peers opened through CUDA IPC)
+    unsigned *flags[kMaxPeers];       // every rank's barrier words: A flags at +0, B flags at +16, generations A / B at +32 / +33,
+                                      // CTA-done counter at +34 (see comm.cu); null = the barriers are separate kernels
+    long long offset;                 // rank * slot
+    long long slot;                   // bytes per rank slot (n_block rounded up to 16)
+    int world, rank;
 };
+
+// ---- peer-memory barrier pieces shared by comm.cu (stand-alone barrier kernel) and scorers.cu (barriers fused into the
+// scoring kernel).  Bounded spins: a rank that never arrives traps the kernel instead of hanging the GPU.
+__device__ __forceinline__ void peer_flag_arrive(const GatherOut &G, int which, unsigned gen) {
+    for (int r = 0; r < G.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[r] + 16 * which + G.rank), "r"(gen) : "memory");
+}
+__device__ __forceinline__ void peer_flag_wait(const GatherOut &G, int which, unsigned gen) {
+    for (int r = 0; r < G.world; ++r) {
+        const unsigned *mine = G.flags[G.rank] + 16 * which + r;
+        unsigned v = 0;
+        for (long long spin = 0; spin < (1ll << 31); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - gen) >= 0) break;
+        }
+        if ((int)(v - gen) < 0) __trap();
+    }
+}
 
 struct DeviceBuf {
     void *p = nullptr;

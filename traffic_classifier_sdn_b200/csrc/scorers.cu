@@ -177,7 +177,9 @@ __device__ __forceinline__ void gnb_prepass_rows(const ScorerParams &P, const fl
     for (int q = 0; q < kRPT; ++q) sure[q] = best_lo[q] > others_hi[q];   // false for NaN / -inf
 }
 
-template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
+// GATHER: the variant whose label stores go to every rank's peer-memory buffer (a separate instantiation: the plain kernel
+// must not pay for it -- with the code compiled in, the 1M-row step went from 10.5 to 11.3 us)
+template <typename T, int D, int R, int KIND, int kThreads, int kRPT, bool GATHER>
 __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_constant__ ScorerParams P,
                                                                 const T *__restrict__ X, int64_t n,
                                                                 int32_t *__restrict__ labels,
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
                                                                 const __grid_constant__ GatherOut G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kTile = kThreads * kRPT;
-    __shared__ __align__(16) unsigned char slab[kTile];   // gathered mode: the tile's labels as bytes
+    __shared__ __align__(16) unsigned char slab[GATHER ? kTile : 16];   // gathered mode: the tile's labels as bytes
     constexpr uint32_t kTileBytes = kTile * D * sizeof(T);
     T *tiles = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kTileBytes);
@@ -206,14 +208,32 @@ __global__ void __launch_bounds__(kThreads) scorer_tiled_kernel(const __grid_con
     // Labels of one tile.  Plain mode: int32 per row.  Gathered mode (G.world > 0): one byte per row, staged in shared memory
     // and written with 16-byte stores into slot [rank] of every rank's gathered buffer -- the all-gather of the label vectors
     // happens HERE, tile by tile over NVLink peer memory, under the streaming of the next rows (comm.cu: tcsdn_predict_gathered).
+    // Gathered mode: barrier A -- "every rank has entered this call", so nobody is still reading the previous vector -- is
+    // ARRIVED at by one thread when the kernel starts and WAITED for by each CTA only before its first store into the peers:
+    // the wait hides behind the first tile's load and scoring.  (Barrier B, "every rank's bytes are out", is a one-warp kernel
+    // behind this one: running it in the last CTA, with a system-scope fence in every CTA, measured slower, 29.7 against
+    // 23 us per step on two GPUs.)  Generations live in device memory: a CUDA graph holding the kernel can be replayed.
+    const bool fusedbar = GATHER && G.world && G.flags[0] != nullptr;
+    unsigned genA = 0;
+    bool a_passed = !fusedbar;
+    if (fusedbar) {
+        genA = G.flags[G.rank][32] + 1;   // stable during the kernel: the barrier-B kernel behind it advances it
+        if (blockIdx.x == 0 && tid == 0) peer_flag_arrive(G, 0, genA);
+    }
     auto store_labels = [&](int64_t row0, const int (&arg)[kRPT]) {
+        if constexpr (GATHER) {
+            if (!a_passed) {
+                if (tid == 0) peer_flag_wait(G, 0, genA);
+                a_passed = true;              // the other threads wait at the __syncthreads below
+            }
+        }
 #pragma unroll
         for (int q = 0; q < kRPT; ++q) {
             const int64_t row = row0 + q * kThreads + tid;
             if (labels && row < n) labels[row] = arg[q];
-            if (G.world) slab[q * kThreads + tid] = row < n ? (unsigned char)arg[q] : (unsigned char)0xFF;
+            if constexpr (GATHER) slab[q * kThreads + tid] = row < n ? (unsigned char)arg[q] : (unsigned char)0xFF;
         }
-        if (G.world) {
+        if constexpr (GATHER) {
             __syncthreads();
             constexpr int kChunks = kTile / 16;
             for (int e = tid; e < kChunks * G.world; e += kThreads) {
@@ -364,12 +384,15 @@ template <typename T, int D, int R, int KIND, int kThreads, int kRPT>
 static int launch_tiled_cfg(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, double *scores, int32_t *flag,
                             cudaStream_t st, int ctas_per_sm, const GatherOut &G) {
     constexpr int kTile = kThreads * kRPT;
-    auto kern = scorer_tiled_kernel<T, D, R, KIND, kThreads, kRPT>;
+    constexpr bool kCanGather = sizeof(T) == 4;   // the fused gather is instantiated for float32 rows (comm.cu checks)
+    if (G.world && !kCanGather) { set_error("fused gather: float32 rows only"); return TCSDN_EINVAL; }
+    auto kern = (kCanGather && G.world) ? scorer_tiled_kernel<T, D, R, KIND, kThreads, kRPT, kCanGather>
+                                        : scorer_tiled_kernel<T, D, R, KIND, kThreads, kRPT, false>;
     const size_t smem = (size_t)kStages * kTile * D * sizeof(T) + kStages * sizeof(uint64_t);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static bool configured[2] = {false, false};  // per instantiation and variant
+    if (!configured[G.world ? 1 : 0]) {
         TCSDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[G.world ? 1 : 0] = true;
     }
     int64_t n_tiles = (n + kTile - 1) / kTile;
     int64_t grid = (int64_t)m->sm_count * ctas_per_sm;
@@ -392,7 +415,7 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
     // GaussianNB (fp64-pipe-bound) wants the constants amortised over 4 rows, the HBM-bound max/min scorers want more warps.
     // Small batches: with 512-row tiles a 1M-row batch is 4.4 tiles per CTA -- the pipeline ramp (first tile) and the tail
     // (some CTAs own one tile more) are a quarter of the step -- so below 16 tiles per CTA the 256-row shape (128 x 2) is used.
-    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 / 3 / 4 forces 128 x 4 / 256 x 2 / 128 x 2 / 128 x 1.
+    // TCSDN_OPT_SCORER_SHAPE = 1 / 2 / 3 forces 128 x 4 / 256 x 2 / 128 x 2 (128 x 1 measured worse: 48 % against 53 %).
     const int per_sm = sizeof(T) == 4 ? 3 : 2;
     int shape = (int)m->opt_scorer_shape;
     if (shape == 0) {
@@ -401,7 +424,6 @@ static int launch_tiled(tcsdn_model *m, const T *x, int64_t n, int32_t *labels, 
     }
     if (shape == 2) return launch_tiled_cfg<T, D, R, KIND, 256, 2>(m, x, n, labels, scores, flag, st, per_sm, G);
     if (shape == 3) return launch_tiled_cfg<T, D, R, KIND, 128, 2>(m, x, n, labels, scores, flag, st, per_sm + 1, G);
-    if (shape == 4) return launch_tiled_cfg<T, D, R, KIND, 128, 1>(m, x, n, labels, scores, flag, st, 2 * per_sm + 2, G);
     return launch_tiled_cfg<T, D, R, KIND, 128, 4>(m, x, n, labels, scores, flag, st, per_sm, G);
 }
 
