@@ -107,10 +107,13 @@ def _build_workload(name, quick=False):
                     bound="hbm", cpu_sample_rows=100_000, visits_per_row=100 * 17.0)
     if name == "forest_hbm2":
         # the regime the "fraction of HBM peak" target is about: the node array (268 MB) does not fit the 126 MB L2
-        spec = synth.random_forest_spec(n_trees=256 if not quick else 32, depth=16, seed=seed + 6, full=True)
+        # (uniform thresholds and uniform rows: every leaf is reached, the walk's working set is the whole array; with
+        # flow-shaped rows the same forest is touched on 58 MB only -- ncu r02 -- and stays in L2)
+        spec = synth.random_forest_spec(n_trees=256 if not quick else 32, depth=16, seed=seed + 6, full=True, uniform=True)
         return dict(spec=spec, sk=None, d=12, rows=1_000_000 if not quick else 100_000, bytes_per_row=52, flops_per_row=0,
-                    desc="adversarial forest, HBM-resident: 256 complete depth-16 trees (33.6M nodes, 268 MB > 126 MB L2), 1M rows",
-                    bound="hbm", cpu_sample_rows=20_000, visits_per_row=256 * 17.0)
+                    desc="adversarial forest, HBM-resident: 256 complete depth-16 trees (33.6M nodes, 268 MB > 126 MB L2), uniform "
+                         "thresholds, 1M rows uniform in [0,1)^12 (every leaf reached)",
+                    bound="hbm", cpu_sample_rows=20_000, visits_per_row=256 * 17.0, rows_kind="uniform")
     if name == "knn":
         Xtr, ytr = synth.make_flows(50_000, seed=seed + 2)
         spec = dict(kind="knn", fit_X=Xtr, y=ytr.astype(np.int32), k=5, classes=synth.CLASSES, n_features=12)
@@ -145,12 +148,17 @@ def sklearn_model(w):
     return sklearn_from_spec(w["spec"])
 
 
-def synth_rows(n, d, seed, device=None):
-    """n float32 rows: a seeded 1M-row synthetic base resampled with replacement (bootstrap) to n rows.  With a device the
+def synth_rows(n, d, seed, device=None, kind="flows"):
+    """kind="uniform": n float32 rows uniform in [0, 1)^d (the HBM-resident forest's cache-hostile input).  Otherwise
+    n float32 rows: a seeded 1M-row synthetic base resampled with replacement (bootstrap) to n rows.  With a device the
     base rows are derived ON the GPU by the reference's own feature derivation (synth.make_flows_device ->
     tcsdn_flow_update); the host variant is the bit-identical closed form."""
     import torch
     from traffic_classifier_sdn_b200 import synth
+    if kind == "uniform":
+        g = torch.Generator().manual_seed(seed)
+        t = torch.rand((n, d), generator=g, dtype=torch.float32)
+        return t.to(device) if device is not None else t
     nb = min(n, 1_000_000)
     if device is not None:
         base = synth.make_flows_device(nb, seed=seed, d=d, dtype="float32", device=device)
@@ -392,7 +400,7 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     row_bytes = 4 * d
     ring = ring_size(rows, row_bytes)
     rank = dist_env()[0]
-    batches = [synth_rows(rows, d, seed=1000 + 17 * rank + i, device=device) for i in range(ring)]
+    batches = [synth_rows(rows, d, seed=1000 + 17 * rank + i, device=device, kind=w.get("rows_kind", "flows")) for i in range(ring)]
     torch.cuda.synchronize()
     lab_dev = torch.empty(rows, dtype=torch.int32, device=device)
     side = torch.cuda.Stream(device=device)
@@ -491,6 +499,36 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     else:
         achieved = rows * w["flops_per_row"] / (kernel_ms * 1e-3) / 1e12
         unit = "TFLOP/s"
+    copy_at_size = None
+    if w["bound"] == "hbm" and rows * w["bytes_per_row"] < (1 << 30) and not extras_light:
+        # context for a launch-scale step: what a plain device copy moving the SAME number of bytes per step reaches when it is
+        # timed the same way (K copies in one CUDA graph, rotating through buffers larger than L2) -- the measured-peak
+        # denominator comes from a 2 GB copy, which amortises the launch; a 36 MB step cannot
+        try:
+            half = rows * w["bytes_per_row"] // 2
+            nbuf = max(2, int(np.ceil(L2_BYTES * 1.25 / (2 * half))) + 1)
+            src = [torch.empty(half, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+            dst = [torch.empty(half, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    dst[i % nbuf].copy_(src[i % nbuf])
+            torch.cuda.synchronize()
+            gcopy = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gcopy, stream=side):
+                for i in range(steps):
+                    dst[i % nbuf].copy_(src[i % nbuf])
+            gcopy.replay()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); gcopy.replay(); c1.record()
+            torch.cuda.synchronize()
+            us = c0.elapsed_time(c1) / steps * 1e3
+            copy_at_size = {"bytes_per_step": 2 * half, "us_per_step": us, "gbs": 2 * half / (us * 1e-6) / 1e9,
+                            "how": "torch copy_ of the same bytes per step, K copies in one CUDA graph"}
+            del gcopy, src, dst
+        except Exception as exc:
+            copy_at_size = {"error": f"{type(exc).__name__}: {exc}"}
     tr = load_traffic(w["name"])
     if tr is not None:
         # the capture was taken on the full-size workload; scale if this run uses another batch size (--quick)
@@ -498,6 +536,10 @@ def measure_gpu(w, steps, warmup, world, device, peaks, extras_light=False, cloc
     roofline = dict(bound=w["bound"], achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
                     traffic=None if tr is None else tr["bytes"], traffic_source=None if tr is None else tr["source"],
                     peak_source=peaks["source"])
+    if copy_at_size is not None:
+        roofline["copy_at_this_size"] = copy_at_size
+        if "gbs" in copy_at_size:
+            roofline["frac_of_copy_at_this_size"] = achieved / copy_at_size["gbs"]
     if w["bound"] == "tensor":
         # next to the algorithmic flops, the flops the tensor cores are actually ISSUED (bf16 x 3 split:
         # K = 80 per pair instead of d = 12, reference rows padded to 64-row tiles) and the ncu tensor-pipe figure
@@ -527,13 +569,24 @@ def _threadpools():
         return [{"error": f"{type(exc).__name__}: {exc}"}]
 
 
-def _svc_pool_predict(sk, X, jobs):
-    """SVC.predict row-chunked over a process pool: libsvm's predict is one serial loop over the rows
-    (sk:svm/src/libsvm/libsvm_helper.c:315-332), so all-core scikit-learn means one chunk per worker process."""
-    from joblib import Parallel, delayed
-    chunks = np.array_split(X, jobs)
-    parts = Parallel(n_jobs=jobs, backend="loky")(delayed(sk.predict)(c) for c in chunks if len(c))
-    return np.concatenate(parts)
+class _SvcPool:
+    """SVC.predict row-chunked over a pool of worker processes: libsvm's predict is one serial loop over the rows
+    (sk:svm/src/libsvm/libsvm_helper.c:315-332), so all-core scikit-learn means one chunk per worker.  The pool is created
+    once (workers and their copy of the model stay alive across calls, like a serving process would keep them)."""
+
+    def __init__(self, sk, jobs):
+        from joblib import Parallel
+        self.sk, self.jobs = sk, jobs
+        self.par = Parallel(n_jobs=jobs, backend="loky")
+        self.par.__enter__()
+
+    def predict(self, X):
+        from joblib import delayed
+        parts = self.par(delayed(self.sk.predict)(c) for c in np.array_split(X, self.jobs) if len(c))
+        return np.concatenate(parts)
+
+    def close(self):
+        self.par.__exit__(None, None, None)
 
 
 def cpu_reference(w, max_seconds=20.0, steps=2, warmup=1):
@@ -546,7 +599,7 @@ def cpu_reference(w, max_seconds=20.0, steps=2, warmup=1):
     kind = w["spec"]["kind"]
     sk = sklearn_model(w)
     n = min(w["cpu_sample_rows"], w["rows"])
-    X = synth_rows(n, w["d"], seed=1000).numpy()
+    X = synth_rows(n, w["d"], seed=1000, kind=w.get("rows_kind", "flows")).numpy()
     if kind != "forest":
         X = X.astype(np.float64)   # sklearn validates these estimators to float64 anyway
     cores = os.cpu_count() or 1
@@ -596,9 +649,12 @@ def cpu_reference(w, max_seconds=20.0, steps=2, warmup=1):
             how = "n_jobs=-1"
         elif kind == "svc":
             try:
-                Xp = synth_rows(min(w["rows"], max(n, jobs * 400)), w["d"], seed=1000).numpy().astype(np.float64)
-                v_all, m_all = run(lambda Z: _svc_pool_predict(sk, Z, jobs), Xp, max_seconds * 0.6)
-                how = f"rows chunked over a pool of {jobs} processes (joblib/loky)"
+                pool = _SvcPool(sk, jobs)
+                Xp = synth_rows(min(w["rows"], max(n, jobs * 300)), w["d"], seed=1000).numpy().astype(np.float64)
+                pool.predict(Xp[: jobs * 4])                      # spawn the workers outside the timed calls
+                v_all, m_all = run(pool.predict, Xp, max(max_seconds * 0.6, 25.0))
+                pool.close()
+                how = f"rows chunked over a pool of {jobs} worker processes (joblib/loky, workers kept alive across calls)"
             except Exception as exc:
                 v_all, m_all, how = v_shipped, m_shipped, f"process pool failed ({type(exc).__name__}: {exc}); single thread"
         else:

@@ -7,3 +7,5 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 timeout 1800 python bench.py > gpurun_out/bench_${TAG}_1gpu.json 2> gpurun_out/bench_${TAG}.stderr; echo "bench rc=$?"
 python tools/show_bench.py gpurun_out/bench_${TAG}_1gpu.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${TAG}_reference_arm.json 2>/dev/null; echo "ref rc=$?"; tail -c 300 gpurun_out/bench_${TAG}_reference_arm.json
+timeout 600 python tools/stress_svc.py 20 2>&1 | tail -1
+bash tools/gpu_profile.sh ${TAG}

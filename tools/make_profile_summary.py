@@ -18,7 +18,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
 summary = {}
 lines = [f"# ncu summaries, round {tag} (B200, --clock-control none; from gpurun_out/prof_{tag}_*.ncu-rep)\n"]
-for name in ("gnb", "logistic", "forest", "forest_hbm", "svc", "knn"):
+for name in ("gnb", "logistic", "forest", "forest_hbm", "forest_hbm2", "svc", "svc_refine", "knn"):
     rep = os.path.join(G, f"prof_{tag}_{name}.ncu-rep")
     if not os.path.exists(rep): continue
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -67,7 +67,7 @@ if os.path.exists(lf):
         k = r[ki][:100]; a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += float(r[vi].replace(',', ''))
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as fh:
-        fh.write(f"# every kernel launch of `python bench.py --steps 5 --warmup 3` under ncu (gpu__time_duration.sum, cold-cache, serialised)\n\n")
+        fh.write(f"# every kernel launch of `python bench.py --steps 5 --warmup 3 --gpu-only` under ncu (gpu__time_duration.sum, cold-cache, serialised)\n\n")
         fh.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write(f"| `{k}` | {c} | {t/1e3:.1f} | {100*t/tot:.1f}% |\n")

@@ -434,7 +434,10 @@ int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t
     const size_t row_bytes = (size_t)d * esz;
     int64_t chunk = m->opt_chunk_rows;
     if (chunk <= 0) {
-        chunk = (int64_t)((16u << 20) / row_bytes);   // ~16 MiB of rows per chunk
+        // ~16 MiB of rows per chunk for the streaming kernels (the copy is their bottleneck: small chunks start the overlap early);
+        // 128 MiB for the distance engine, whose persistent CTAs take 512 rows each and want several passes per launch
+        const size_t chunk_bytes = (m->kind == TCSDN_KIND_KNN || m->kind == TCSDN_KIND_SVC) ? (128u << 20) : (16u << 20);
+        chunk = (int64_t)(chunk_bytes / row_bytes);
         chunk = (chunk / 1024) * 1024;
         if (chunk < 1024) chunk = 1024;
     }

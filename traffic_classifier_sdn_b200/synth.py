@@ -113,7 +113,7 @@ def make_flows_device(n: int, seed: int = 0, d: int = 12, dtype="float32", devic
     return feat
 
 
-def _full_tree(rng, depth, d, n_classes, impure, scale):
+def _full_tree(rng, depth, d, n_classes, impure, scale, uniform=False):
     """Complete binary tree in preorder, vectorised: node i at level l has left = i+1, right = i + 2^(depth-l)."""
     n = (1 << (depth + 1)) - 1
     level = np.zeros(n, np.int32)
@@ -127,7 +127,10 @@ def _full_tree(rng, depth, d, n_classes, impure, scale):
     left = np.where(leaf, -1, idx + 1).astype(np.int32)
     right = np.where(leaf, -1, idx + (1 << (depth - level).astype(np.int64))).astype(np.int32)
     feat = np.where(leaf, -2, rng.integers(0, d, n)).astype(np.int32)
-    thr = np.abs(rng.normal(0.0, 1.0, n)) * scale[np.maximum(feat, 0)] * 0.7 + np.where(rng.random(n) < 0.5, 0.5, 0.0)
+    if uniform:   # thresholds uniform in [0, 1): rows uniform in [0, 1)^d spread over ALL leaves (cache-hostile by construction)
+        thr = rng.random(n)
+    else:
+        thr = np.abs(rng.normal(0.0, 1.0, n)) * scale[np.maximum(feat, 0)] * 0.7 + np.where(rng.random(n) < 0.5, 0.5, 0.0)
     thr = np.where(leaf, -2.0, thr)
     val = np.full((n, n_classes), 1.0 / n_classes)
     nl = int(leaf.sum())
@@ -144,15 +147,17 @@ def _full_tree(rng, depth, d, n_classes, impure, scale):
 
 
 def random_forest_spec(n_trees: int, depth: int, d: int = 12, n_classes: int = 6, seed: int = 0, full: bool = True,
-                       impure: float = 0.05, scale=None):
+                       impure: float = 0.05, scale=None, uniform: bool = False):
     """A synthetic forest spec (modelio layout) with random splits: `full` = complete binary trees of the given
-    depth (the adversarial, cache-hostile forest of SURVEY 8d); otherwise ragged trees that stop early at random."""
+    depth (the adversarial, cache-hostile forest of SURVEY 8d); otherwise ragged trees that stop early at random.
+    `uniform` (full trees): thresholds uniform in [0, 1) -- with rows uniform in [0, 1)^d every leaf is reached, so the
+    walk touches the WHOLE node array (flow-shaped rows follow a few paths only and leave most of a random tree cold)."""
     rng = np.random.default_rng(seed)
     scale = np.asarray(scale if scale is not None else [24, 2076, 24, 122, 2069, 9651, 27, 2977, 27, 17, 2974, 2441][:d], float)
     lefts, rights, feats, thrs, vals, offs = [], [], [], [], [], [0]
     for _ in range(n_trees):
         if full:
-            l, r, f, t, v = _full_tree(rng, depth, d, n_classes, impure, scale)
+            l, r, f, t, v = _full_tree(rng, depth, d, n_classes, impure, scale, uniform)
             lefts.append(l); rights.append(r); feats.append(f); thrs.append(t); vals.append(v)
             offs.append(offs[-1] + len(l))
             continue
