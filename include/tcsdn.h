@@ -134,6 +134,11 @@ int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
 int tcsdn_predict(tcsdn_model_t *m, const void *x, int64_t n, int32_t d, int32_t x_dtype,
                   int32_t x_loc, int32_t *labels_out, double *scores_out, void *cuda_stream);
 
+/* Host tail of `model.predict`: out[i] = table[idx[i]] for fixed-width class labels (numpy `classes_.take(idx)`,
+ * sk:linear_model/_base.py:423), item_bytes bytes per label, gathered on up to n_threads host threads.  Host pointers. */
+int tcsdn_take_labels(const int32_t *idx, int64_t n, const void *table, int32_t n_items, int32_t item_bytes, void *out,
+                      int32_t n_threads);
+
 /* After device-pointer predicts: synchronise `cuda_stream` and report TCSDN_ENONFINITE if any predict since the
  * last check saw NaN/inf rows (the flag is sticky and cleared here; host-pointer predicts check themselves). */
 int tcsdn_sync_check(tcsdn_model_t *m, void *cuda_stream);

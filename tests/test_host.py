@@ -206,3 +206,34 @@ def test_logistic_proba_forms_match_sklearn():
     sk.multi_class = "ovr"            # attribute of scikit-learn <= 1.6 estimators (the reference's pickles are 1.0.1)
     assert modelio.spec_from_estimator(sk)["ovr"] is True
     assert np.allclose(lr_proba(np.full((2, 3), -1e4), True), 1.0 / 3)   # all-zero sigmoids -> uniform
+
+
+def test_take_labels_matches_numpy_take():
+    """tcsdn_take_labels (the host tail of predict on large batches) == classes_.take(idx) for fixed-width label dtypes;
+    out-of-range indices are an error, not a wild read"""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for cls in (np.array(["dns", "game", "ping", "quake", "telnet", "voice"]), np.arange(7, dtype=np.int64), np.array([b"a", b"bcd"])):
+        idx = rng.integers(0, len(cls), 300_001).astype(np.int32)
+        out = np.empty(len(idx), dtype=cls.dtype)
+        for threads in (1, 5):
+            out[:] = cls[0]
+            assert lib.tcsdn_take_labels(_lib.ptr(idx), len(idx), _lib.ptr(cls), len(cls), cls.dtype.itemsize, _lib.ptr(out), threads) == 0
+            assert np.array_equal(out, cls.take(idx))
+        idx[1234] = len(cls)
+        assert lib.tcsdn_take_labels(_lib.ptr(idx), len(idx), _lib.ptr(cls), len(cls), cls.dtype.itemsize, _lib.ptr(out), 3) == _lib.EINVAL
+    assert lib.tcsdn_take_labels(None, 0, None, 1, 4, None, 1) == 0
+
+
+def test_synthetic_counters_are_consistent_with_the_closed_form():
+    """synth.make_flows(counters=True) exposes the cumulative counters behind the rows (the input of the GPU generator
+    make_flows_device): deltas, instantaneous and average rates recomputed from them equal the closed-form rows"""
+    from traffic_classifier_sdn_b200 import synth
+    X, y = synth.make_flows(5000, seed=3)
+    Cn, y2 = synth.make_flows(5000, seed=3, counters=True)
+    assert np.array_equal(y, y2) and Cn.shape == (5000, 9)
+    age = Cn[:, 0]
+    for base, cols in ((1, (0, 1, 2, 3, 4, 5)), (5, (6, 7, 8, 9, 10, 11))):
+        dp, db = Cn[:, base + 2] - Cn[:, base], Cn[:, base + 3] - Cn[:, base + 1]
+        ref = np.column_stack([dp, db, dp, Cn[:, base + 2] / age, db, Cn[:, base + 3] / age])
+        assert np.array_equal(ref, X[:, cols])

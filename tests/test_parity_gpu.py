@@ -127,6 +127,21 @@ def test_wrong_feature_count_and_nonfinite_raise(models):
         bad[513, 4] = np.inf
         with pytest.raises(ValueError, match="NaN|infinity"):
             models[kind].predict(bad.astype(np.float32))
+        # -inf in every feature position: in the forest a -inf used to satisfy `v <= -inf` at a leaf / halt node and run the
+        # walk out of its group (sticky illegal address or an endless spin); it must raise like the others, in both dtypes,
+        # on the shared-memory walker and -- huge float64 values overflow to -inf in the float32 cast -- through the cast
+        for col in (0, 6, 11):
+            bad = np.ones((1500, 12))
+            bad[1027, col] = -np.inf
+            with pytest.raises(ValueError, match="NaN|infinity"):
+                models[kind].predict(bad)
+            with pytest.raises(ValueError, match="NaN|infinity"):
+                models[kind].predict(bad.astype(np.float32))
+        if kind == "forest":
+            bad = np.ones((300, 12))
+            bad[7, 3] = -1e300                    # finite float64, -inf after sklearn's cast to float32: sklearn raises too
+            with pytest.raises(ValueError, match="NaN|infinity"):
+                models[kind].predict(bad)
         with pytest.raises(ValueError, match="2D"):
             models[kind].predict(np.zeros(12))
         assert models[kind].predict(np.ones((2, 12))).shape == (2,)  # still usable afterwards
@@ -191,6 +206,14 @@ def test_forest_synthetic_vs_oracle(cfg):
     assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
     idx32, pr32 = est._run(X.astype(np.float32), True)
     assert np.array_equal(pr32, rpr)
+    # non-finite rows on every walker (shared-memory groups, trees walked in L2/HBM, both CTA shapes): the call raises
+    # and the handle stays usable
+    for bad_value in (-np.inf, np.inf, np.nan):
+        Xb = X[:3000].copy()
+        Xb[1234, 5] = bad_value
+        with pytest.raises(ValueError, match="NaN|infinity"):
+            est.predict(Xb)
+    assert np.array_equal(est.predict_indices(X), ridx)
 
 
 def test_forest_threshold_boundary_values():

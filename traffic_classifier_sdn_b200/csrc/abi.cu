@@ -1,8 +1,10 @@
 // abi.cu -- the C ABI of libtcsdn.so (include/tcsdn.h): handle life cycle, model packing to HBM,
 // the predict dispatcher and the host-pointer pipeline.  No kernel lives here.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <thread>
 
 #include "common.h"
 
@@ -555,6 +557,38 @@ int tcsdn_svc_ovr_from_ovo(const double *dec, int64_t n, int32_t n_classes, int3
     if (rc == TCSDN_OK && cudaMemcpy(out, d_out, (size_t)n * n_classes * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = TCSDN_ECUDA; }
     cudaFree(d_dec); cudaFree(d_out);
     return rc;
+}
+
+/* classes_.take(idx) for fixed-width class labels (sk:linear_model/_base.py:423): a gather of item_bytes-wide items on a few host
+ * threads.  For a million rows and '<U6' names (24 bytes) numpy's take costs more host time than the H2D copy and the
+ * kernel together; this is the host tail of the public predict, nothing else. */
+int tcsdn_take_labels(const int32_t *idx, int64_t n, const void *table, int32_t n_items, int32_t item_bytes, void *out,
+                      int32_t n_threads) {
+    if (n < 0 || n_items < 1 || item_bytes < 1 || (n > 0 && (!idx || !table || !out))) { set_error("take_labels: bad arguments"); return TCSDN_EINVAL; }
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if ((int64_t)n_threads > n / 65536 + 1) n_threads = (int32_t)(n / 65536 + 1);
+    std::atomic<int> bad{0};
+    auto work = [&](int64_t lo, int64_t hi) {
+        const char *tab = static_cast<const char *>(table);
+        char *o = static_cast<char *>(out);
+        const size_t w = (size_t)item_bytes;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t k = idx[i];
+            if (k < 0 || k >= n_items) { bad.store(1); return; }
+            memcpy(o + (size_t)i * w, tab + (size_t)k * w, w);
+        }
+    };
+    if (n_threads == 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        const int64_t per = (n + n_threads - 1) / n_threads;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(work, std::min<int64_t>(n, t * per), std::min<int64_t>(n, (t + 1) * per));
+        for (auto &t : th) t.join();
+    }
+    if (bad.load()) { set_error("take_labels: class index out of range"); return TCSDN_EINVAL; }
+    return TCSDN_OK;
 }
 
 int tcsdn_flow_update(double *state, const double *packets, const double *bytes, const double *curr_time,

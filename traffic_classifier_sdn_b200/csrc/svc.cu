@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(kSvcThreads) svc_exact12_kernel(const T *__res
                     }
                     __syncthreads();
                     if (live) {
-                        for (int tt = 0; tt < tn; ++tt) {
+                        // two support vectors per iteration: two independent distance chains and two exp() in flight (the loop
+                        // is a latency chain on the fp64 pipe), their contributions added in index order as before
+                        auto dist = [&](int tt) {
                             const double2 *sp = reinterpret_cast<const double2 *>(ss + tt * D);
                             double sum = 0.0;
 #pragma unroll
@@ -215,7 +217,9 @@ __global__ void __launch_bounds__(kSvcThreads) svc_exact12_kernel(const T *__res
                                 df = x[2 * j2 + 1] - t.y;
                                 sum = fma(df, df, sum);
                             }
-                            const double kv = exp(-gamma * sum);
+                            return sum;
+                        };
+                        auto add = [&](int tt, double kv) {
                             const double2 *cp = reinterpret_cast<const double2 *>(cs + tt * 8);
 #pragma unroll
                             for (int m2 = 0; m2 < (Cm1 + 1) / 2; ++m2) {
@@ -223,7 +227,15 @@ __global__ void __launch_bounds__(kSvcThreads) svc_exact12_kernel(const T *__res
                                 acc[2 * m2] = fma(c2.x, kv, acc[2 * m2]);
                                 if (2 * m2 + 1 < Cm1) acc[2 * m2 + 1] = fma(c2.y, kv, acc[2 * m2 + 1]);
                             }
+                        };
+                        int tt = 0;
+                        for (; tt + 1 < tn; tt += 2) {
+                            const double s0 = dist(tt), s1 = dist(tt + 1);
+                            const double k0 = exp(-gamma * s0), k1 = exp(-gamma * s1);
+                            add(tt, k0);
+                            add(tt + 1, k1);
                         }
+                        if (tt < tn) add(tt, exp(-gamma * dist(tt)));
                     }
                 }
                 // class ci is done: row mm belongs to the pair (ci, opponent), opponent = mm < ci ? mm : mm + 1; the lower

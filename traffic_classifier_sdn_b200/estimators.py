@@ -225,18 +225,18 @@ class _Base:
 
     def _labels_from_indices(self, idx):
         """classes_.take(idx) (sk:linear_model/_base.py:423): string class names make this a 4-byte read and a 24-byte write
-        per row -- on a million-row batch more host time than the H2D copy and the kernel together -- so large batches
-        are gathered in slices on a few threads (numpy releases the GIL inside take)."""
+        per row -- on a million-row batch more host time than the H2D copy and the kernel together -- so large batches of
+        fixed-width labels are gathered by the library on a few host threads (tcsdn_take_labels)."""
         n = len(idx)
-        if n < (1 << 18):
-            return self.classes_.take(idx)
+        cls = self.classes_
+        if n < (1 << 16) or cls.dtype.hasobject or cls.dtype.itemsize == 0:
+            return cls.take(idx)
         import os
-        from concurrent.futures import ThreadPoolExecutor
-        out = np.empty(n, dtype=self.classes_.dtype)
-        workers = max(1, min(16, (os.cpu_count() or 1) // 2, n >> 17))
-        bounds = np.linspace(0, n, workers + 1).astype(np.int64)
-        with ThreadPoolExecutor(workers) as pool:
-            list(pool.map(lambda k: np.take(self.classes_, idx[bounds[k]:bounds[k + 1]], out=out[bounds[k]:bounds[k + 1]]), range(workers)))
+        table = np.ascontiguousarray(cls)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty(n, dtype=table.dtype)
+        _lib.check(_lib.load().tcsdn_take_labels(_lib.ptr(idx), n, _lib.ptr(table), len(table), table.dtype.itemsize, _lib.ptr(out),
+                                                 max(1, min(16, (os.cpu_count() or 2) // 2))))
         return out
 
     def _scores(self, X):
