@@ -7,6 +7,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 timeout 1800 python bench.py > gpurun_out/bench_${TAG}_1gpu.json 2> gpurun_out/bench_${TAG}.stderr; echo "bench rc=$?"
 python tools/show_bench.py gpurun_out/bench_${TAG}_1gpu.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${TAG}_reference_arm.json 2>/dev/null; echo "ref rc=$?"
+if [ "${2:-launches}" = launches ]; then
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 5 --warmup 3 --gpu-only > gpurun_out/launches_${TAG}.stdout 2> gpurun_out/launches_${TAG}.stderr
 python - <<PY
 import csv, collections
@@ -25,3 +26,5 @@ with open("gpurun_out/${TAG}_launches.md", "w") as fh:
         fh.write(f"| \`{k}\` | {c} | {t/1e3:.1f} | {100*t/tot:.1f}% |\n")
 print(open("gpurun_out/${TAG}_launches.md").read()[:3000])
 PY
+fi
+timeout 120 tools/tmem_probe > gpurun_out/${TAG}_probe.txt 2>&1; tail -3 gpurun_out/${TAG}_probe.txt

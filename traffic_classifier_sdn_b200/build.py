@@ -9,6 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtcsdn.so")
 SOURCES = ["abi.cu", "scorers.cu", "forest.cu", "knn.cu", "svc.cu", "flow.cu", "dist_engine.cu", "comm.cu", "fit.cu"]
+# scorers.cu is compiled five times: once as the dispatcher and once per tiled feature count (object name -> extra flags)
+VARIANTS = {"scorers.cu": [("scorers.o", []), ("scorers_d4.o", ["-DTCSDN_SCORER_D=4"]), ("scorers_d8.o", ["-DTCSDN_SCORER_D=8"]),
+                           ("scorers_d12.o", ["-DTCSDN_SCORER_D=12"]), ("scorers_d16.o", ["-DTCSDN_SCORER_D=16"])]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -42,9 +45,11 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     env.pop("CXX", None)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
+        for objname, vflags in VARIANTS.get(src, [(src.replace(".cu", ".o"), [])]):
+            obj = os.path.join(objdir, objname)
+            cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + list(extra_flags) + vflags + ["-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((f"{src} {' '.join(vflags)}".strip(), obj,
+                          subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
     objs, log = [], []
     for src, obj, p in procs:
         out = p.communicate()[0]

@@ -65,20 +65,26 @@ struct GatherOut {
 };
 
 // ---- peer-memory barrier pieces shared by comm.cu (stand-alone barrier kernel) and scorers.cu (barriers fused into the
-// scoring kernel).  Bounded spins: a rank that never arrives traps the kernel instead of hanging the GPU.
+// scoring kernel).  Bounded waits (two minutes): a rank that never arrives traps the kernel instead of hanging the GPU.
 __device__ __forceinline__ void peer_flag_arrive(const GatherOut &G, int which, unsigned gen) {
     for (int r = 0; r < G.world; ++r)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(G.flags[r] + 16 * which + G.rank), "r"(gen) : "memory");
 }
 __device__ __forceinline__ void peer_flag_wait(const GatherOut &G, int which, unsigned gen) {
+    unsigned long long t0 = 0;
     for (int r = 0; r < G.world; ++r) {
         const unsigned *mine = G.flags[G.rank] + 16 * which + r;
         unsigned v = 0;
-        for (long long spin = 0; spin < (1ll << 31); ++spin) {
+        for (long long spin = 0;; ++spin) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
             if ((int)(v - gen) >= 0) break;
+            if ((spin & 4095) == 4095) {   // a peer that has not arrived after two minutes is gone: fail the launch, do not hang the GPU
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 120000000000ull) __trap();
+            }
         }
-        if ((int)(v - gen) < 0) __trap();
     }
 }
 

@@ -440,6 +440,23 @@ static int dispatch_rows(tcsdn_model *m, const T *x, int64_t n, int32_t *labels,
     return TCSDN_EINVAL;
 }
 
+// The tiled kernels are instantiated per feature count in separate translation units (the same source compiled with
+// -DTCSDN_SCORER_D=4 / 8 / 12 / 16: four compiler processes instead of one, build.py); the unit without the macro holds the
+// generic kernel and the dispatcher.
+#ifndef TCSDN_SCORER_D
+#define TCSDN_SCORER_D 0
+#endif
+
+#define TCSDN_DECLARE_D(DD)                                                                                                       \
+    int scorer_dispatch_f32_d##DD(tcsdn_model *m, int kind, const float *x, int64_t n, int32_t *labels, double *scores, int32_t *flag, \
+                                  cudaStream_t st, const GatherOut &G);                                                            \
+    int scorer_dispatch_f64_d##DD(tcsdn_model *m, int kind, const double *x, int64_t n, int32_t *labels, double *scores, int32_t *flag, \
+                                  cudaStream_t st, const GatherOut &G);
+TCSDN_DECLARE_D(4) TCSDN_DECLARE_D(8) TCSDN_DECLARE_D(12) TCSDN_DECLARE_D(16)
+#undef TCSDN_DECLARE_D
+
+#if TCSDN_SCORER_D != 0
+
 template <typename T, int D>
 static int dispatch_kind(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
                          int32_t *flag, cudaStream_t st, const GatherOut &G) {
@@ -448,16 +465,42 @@ static int dispatch_kind(tcsdn_model *m, int kind, const T *x, int64_t n, int32_
     return dispatch_rows<T, D, KIND_AFFINE_MAX>(m, x, n, labels, scores, flag, st, G);
 }
 
+#define TCSDN_CAT2(a, b) a##b
+#define TCSDN_CAT(a, b) TCSDN_CAT2(a, b)
+int TCSDN_CAT(scorer_dispatch_f32_d, TCSDN_SCORER_D)(tcsdn_model *m, int kind, const float *x, int64_t n, int32_t *labels, double *scores,
+                                                     int32_t *flag, cudaStream_t st, const GatherOut &G) {
+    return dispatch_kind<float, TCSDN_SCORER_D>(m, kind, x, n, labels, scores, flag, st, G);
+}
+int TCSDN_CAT(scorer_dispatch_f64_d, TCSDN_SCORER_D)(tcsdn_model *m, int kind, const double *x, int64_t n, int32_t *labels, double *scores,
+                                                     int32_t *flag, cudaStream_t st, const GatherOut &G) {
+    return dispatch_kind<double, TCSDN_SCORER_D>(m, kind, x, n, labels, scores, flag, st, G);
+}
+
+#else   // ---- the dispatcher unit
+
+static int dispatch_d(tcsdn_model *m, int kind, const float *x, int64_t n, int32_t *l, double *s, int32_t *f, cudaStream_t st, const GatherOut &G) {
+    switch (m->d) {
+        case 4: return scorer_dispatch_f32_d4(m, kind, x, n, l, s, f, st, G);
+        case 8: return scorer_dispatch_f32_d8(m, kind, x, n, l, s, f, st, G);
+        case 12: return scorer_dispatch_f32_d12(m, kind, x, n, l, s, f, st, G);
+        default: return scorer_dispatch_f32_d16(m, kind, x, n, l, s, f, st, G);
+    }
+}
+static int dispatch_d(tcsdn_model *m, int kind, const double *x, int64_t n, int32_t *l, double *s, int32_t *f, cudaStream_t st, const GatherOut &G) {
+    switch (m->d) {
+        case 4: return scorer_dispatch_f64_d4(m, kind, x, n, l, s, f, st, G);
+        case 8: return scorer_dispatch_f64_d8(m, kind, x, n, l, s, f, st, G);
+        case 12: return scorer_dispatch_f64_d12(m, kind, x, n, l, s, f, st, G);
+        default: return scorer_dispatch_f64_d16(m, kind, x, n, l, s, f, st, G);
+    }
+}
+
 template <typename T>
 static int launch_scorer_t(tcsdn_model *m, int kind, const T *x, int64_t n, int32_t *labels, double *scores,
                            int32_t *flag, cudaStream_t st, const GatherOut &G) {
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    if (m->sp_valid && aligned && m->opt_engine != 1) {
-        if (m->d == 12) return dispatch_kind<T, 12>(m, kind, x, n, labels, scores, flag, st, G);
-        if (m->d == 8) return dispatch_kind<T, 8>(m, kind, x, n, labels, scores, flag, st, G);
-        if (m->d == 16) return dispatch_kind<T, 16>(m, kind, x, n, labels, scores, flag, st, G);
-        if (m->d == 4) return dispatch_kind<T, 4>(m, kind, x, n, labels, scores, flag, st, G);
-    }
+    if (m->sp_valid && aligned && m->opt_engine != 1 && (m->d == 4 || m->d == 8 || m->d == 12 || m->d == 16))
+        return dispatch_d(m, kind, x, n, labels, scores, flag, st, G);
     if (G.world) { set_error("fused gather needs the tiled scorer (d in {4, 8, 12, 16}, <= 8 score rows, 16-byte aligned rows)"); return TCSDN_EINVAL; }
     int64_t blocks = (n + 255) / 256;
     int64_t cap = (int64_t)m->sm_count * 8;
@@ -479,5 +522,7 @@ int launch_scorer(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *
     if (dtype == TCSDN_F32) return launch_scorer_t<float>(m, kind, static_cast<const float *>(x), n, labels, scores, flag, st, G);
     return launch_scorer_t<double>(m, kind, static_cast<const double *>(x), n, labels, scores, flag, st, G);
 }
+
+#endif   // TCSDN_SCORER_D
 
 }  // namespace tcsdn
