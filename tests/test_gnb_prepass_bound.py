@@ -1,6 +1,7 @@
 """CPU check of the mathematics behind the GaussianNB fp32 pre-pass (csrc/scorers.cu, gnb_prepass_rows).
 
-The kernel evaluates  acc~_c = c~_c - sum_j fma32(x_j, a~_cj, -b~_cj)^2  in fp32 and claims
+The kernel evaluates  T~_c = sum_j fma32(x_j, a~_cj, -b~_cj)^2  (fp32 fma chain, two rows per FFMA2) and
+acc~_c = c~_c - T~_c  in fp32 and claims
     |acc~_c - jll_c| <= E_c = 2^-19 (T_c + |c_c| + sum_j b_cj^2),   T_c = c~_c - acc~_c,
 where jll_c is the fp64 definition.  A row is certified when the class with the largest upper bound acc~ + E has a
 lower bound acc~ - E above every other class's upper bound; then the fp64 argmax must be that class.  This test
@@ -30,11 +31,12 @@ def _fp64(x, a, b, c):
 
 def _fp32(x, a, b, c):
     af, bf, cf = a.astype(np.float32), b.astype(np.float32), c.astype(np.float32)
-    acc = np.broadcast_to(cf[None], (len(x), len(c))).astype(np.float32).copy()
+    Tacc = np.zeros((len(x), len(c)), np.float32)
     xf = x.astype(np.float32)
     for j in range(x.shape[1]):
         t = (xf[:, None, j].astype(np.float64) * af[None, :, j].astype(np.float64) - bf[None, :, j].astype(np.float64)).astype(np.float32)
-        acc = (acc.astype(np.float64) - t.astype(np.float64) * t.astype(np.float64)).astype(np.float32)
+        Tacc = (Tacc.astype(np.float64) + t.astype(np.float64) * t.astype(np.float64)).astype(np.float32)
+    acc = (cf[None].astype(np.float64) - Tacc.astype(np.float64)).astype(np.float32)
     T = cf[None].astype(np.float64) - acc.astype(np.float64)
     E = EPS * (T + np.abs(c)[None] + np.sum(b * b, axis=1)[None])
     return acc.astype(np.float64), E
