@@ -69,7 +69,9 @@ enum { /* tcsdn_set_option() keys */
     TCSDN_OPT_SCORER_SHAPE = 4,    /* streaming scorers' CTA shape: 0 auto, 1 = 128 threads x 4 rows, 2 = 256 x 2, 3 = 128 x 2 */
     TCSDN_OPT_FOREST_SHAPE = 5,    /* forest CTA shape: 0 auto, 1 = 512 threads x 2 rows, 2 = 256 x 4, 3 = 1024 x 1 */
     TCSDN_OPT_FOREST_SORT = 6,     /* 1 (default): re-assign a tile's rows to threads in tree-0 leaf order */
-    TCSDN_OPT_KNN_FLUSH_TILES = 7  /* knn engine: reference tiles between two exact-evaluation rounds, 1..31; 0 = default */
+    TCSDN_OPT_KNN_FLUSH_TILES = 7, /* knn engine: reference tiles between two exact-evaluation rounds, 1..31; 0 = default */
+    TCSDN_OPT_KNN_PRUNE = 8        /* knn engine: 0 (default) queries sorted by home tile and far tiles left out, 1 = every tile
+                                      for every query (the unpruned engine; results are identical) */
 };
 
 int tcsdn_version(void);
@@ -124,9 +126,10 @@ int tcsdn_model_score_cols(const tcsdn_model_t *m);
 int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value);
 /* counters of the last predict on this handle: [0] kernels launched, [1] rows through the tensor-core
  * engine, [2] rows through the fp64 CUDA-core kernels, [3] exact fp64 re-evaluations of the knn filter (cumulative
- * since create), [5] largest observed |tensor-core value - exact| / (the error model's denominator), times 2^40
+ * since create), [4] knn engine: reference tiles multiplied per 512-row pass, times 1000 (cumulative average), [5] largest observed |tensor-core value - exact| / (the error model's denominator), times 2^40
  * (cumulative, audit mode), [6] rows a certified fast path could not decide and handed to the fp64 definition
- * (GaussianNB fp32 pre-pass, svc engine; cumulative since create); rest reserved.  out has 8 slots.  Reading the
+ * (GaussianNB fp32 pre-pass, svc engine; cumulative since create), [7] knn engine: rows whose label depended on a tie at
+ * the k-th distance and were re-run by the index-order fp64 kernel (cumulative).  out has 8 slots.  Reading the
  * device-side counters synchronises the device.  Concurrent predicts on one handle add up in [0..2]. */
 int tcsdn_model_stats(const tcsdn_model_t *m, int64_t *out);
 

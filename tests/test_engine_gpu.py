@@ -89,11 +89,63 @@ def test_knn_engine_lattice_ties_heap_order():
     idx, pr = est._run(q, True)
     ridx, rpr = oracle.knn(spec, q)
     assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+    # the engine visits tiles nearest-first; rows whose class counts depend on WHICH of several equally distant rows sklearn's
+    # index-order heap keeps are handed to the index-order kernel (stats[7]) -- on a 3^4 lattice that is most of them
+    assert est.stats()[7] > 0
     from sklearn.neighbors import KNeighborsClassifier
     from threadpoolctl import threadpool_limits
     with threadpool_limits(limits=1):
         sk = KNeighborsClassifier(5, algorithm="brute").fit(tr, y)
         assert np.array_equal(pr, sk.predict_proba(q))
+
+
+@pytest.mark.parametrize("nt,nq,k", [(20000, 40000, 5), (5000, 9000, 3), (130, 5000, 7)])
+def test_knn_engine_pruned_equals_unpruned_and_oracle(nt, nq, k):
+    """queries sorted by home tile + far tiles left out (the default) against every-tile-for-every-query (option 8 = 1) and the
+    oracle: identical labels and probabilities; the pruned run multiplies fewer tiles per pass and evaluates no more pairs"""
+    spec = _knn_spec(nt, k=k, seed=nt + 3)
+    Xq = synth.make_flows(nq, seed=nq + 7, return_labels=False)
+    Xq[:100] = spec["fit_X"][:100]
+    ridx, rpr = oracle.knn(spec, Xq)
+    n_tiles = -(-nt // 64)
+    seen = {}
+    for off in (0, 1):
+        est = _force(from_spec(spec), 2)
+        est.set_option(_lib.OPT_KNN_PRUNE, off)
+        idx, pr = est._run(Xq, True)
+        st = est.stats()
+        assert st[1] == nq and st[2] == 0
+        assert np.array_equal(idx, ridx) and np.array_equal(pr, rpr), f"prune_off={off}"
+        seen[off] = (st[4] / 1000.0, st[3] / nq, st[7])
+    print(f"knn nt={nt} k={k}: tiles per pass pruned {seen[0][0]:.1f} / unpruned {seen[1][0]:.1f} of {n_tiles}; "
+          f"exact evaluations per query {seen[0][1]:.1f} / {seen[1][1]:.1f}; tie rows {seen[0][2]} / {seen[1][2]}")
+    assert abs(seen[1][0] - n_tiles) < 1e-6
+    assert seen[0][0] <= n_tiles
+    if nt >= 20000:
+        assert seen[0][0] < 0.8 * n_tiles, "clustered flow rows, dense queries: the pruned pass should leave tiles out"
+
+
+def test_knn_engine_class_relevant_ties_go_to_index_order_kernel():
+    """twin training rows with DIFFERENT classes and k = 1: the label is whichever twin sklearn's heap keeps (the first); twins
+    with the SAME class need no second opinion"""
+    rng = np.random.default_rng(5)
+    base = rng.normal(0, 100.0, (3000, 12))
+    tr = np.concatenate([base, base[:500]])                  # 500 rows have an exact twin (index + 3000)
+    y = rng.integers(0, 4, len(tr)).astype(np.int32)
+    y[3000:3250] = y[:250]                                   # ... half of the twins agree on the class
+    y[3250:3500] = (y[250:500] + 1) % 4                      # ... half do not
+    q = np.concatenate([base[:500], rng.normal(0, 100.0, (4000, 12))])
+    spec = dict(kind="knn", fit_X=tr, y=y, k=1, classes=np.arange(4), n_features=12)
+    est = _force(from_spec(spec), 2)
+    idx, pr = est._run(q, True)
+    ridx, rpr = oracle.knn(spec, q)
+    assert np.array_equal(pr, rpr) and np.array_equal(idx, ridx)
+    # expected: queries whose nearest distance is shared by rows of different classes (the 250 disagreeing twins themselves,
+    # and every other query whose nearest neighbour happens to be such a pair)
+    d2 = ((q[:, None, :] - tr[None, :, :]) ** 2).sum(2)
+    near = d2 == d2.min(1, keepdims=True)
+    expect = sum(len(set(y[np.flatnonzero(r)])) > 1 for r in near)
+    assert expect >= 250 and est.stats()[7] == expect, (expect, est.stats())
 
 
 def test_knn_engine_equals_fp64_kernel_on_golden(golden, specs):

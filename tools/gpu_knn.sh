@@ -1,8 +1,6 @@
 #!/bin/bash
-# KNN engine check: engine + parity tests, then the flush-period sweep on the 10M x 50k workload
+# KNN engine: parity tests, then the 10M x 50k workload's time with pruning on and off and the engine's own counters
+# (tiles multiplied per pass, tie rows, exact evaluations)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_engine_gpu.py tests/test_parity_gpu.py -m gpu -q -x -k "knn or KNN or kneigh or engine" > gpurun_out/pytest_knn.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/pytest_knn.log
-for f in ${KNN_FLUSH_LIST:-8 16 31}; do
-  echo "flush $f: $(TCSDN_TOOL_OPTS=7=$f timeout 300 python tools/run_workload.py knn 10000000 2 2>&1 | tail -1)"
-done
+timeout 600 python -m pytest tests/test_engine_gpu.py -q --timeout 150 -k "knn or engine_ragged or nonfinite or full_size_properties" 2>&1 | tail -25
+timeout 300 python tools/knn_time.py "$@" 2>&1 | tail -12

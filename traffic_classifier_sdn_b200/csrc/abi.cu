@@ -384,6 +384,7 @@ int tcsdn_set_option(tcsdn_model_t *m, int32_t key, int64_t value) {
         case TCSDN_OPT_KNN_FLUSH_TILES:
             if (value < 0 || value > 31) { set_error("knn flush tiles must be 0..31"); return TCSDN_EINVAL; }
             m->opt_knn_flush = value; return TCSDN_OK;
+        case TCSDN_OPT_KNN_PRUNE: m->opt_knn_prune = value ? 1 : 0; return TCSDN_OK;
     }
     set_error("unknown option key %d", key);
     return TCSDN_EINVAL;

@@ -122,6 +122,7 @@ struct tcsdn_model {
     int64_t opt_forest_shape = 0;    // 0 auto (1024 x 1; 512 x 2 when trees are walked in HBM), 1 = 512 x 2, 2 = 256 x 4, 3 = 1024 x 1
     int64_t opt_forest_sort = 1;     // coherence sort on/off
     int64_t opt_knn_flush = 0;       // tiles between two evaluation rounds of the knn engine; 0 = default
+    int64_t opt_knn_prune = 0;       // 1 = knn engine visits every tile for every query
     // counters of the last predict; atomics because several host threads may predict on one handle (they then add up)
     std::atomic<int64_t> stats[8] = {};
 
@@ -173,6 +174,9 @@ int launch_forest(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *
                   int32_t *flag, cudaStream_t st);
 int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
                      int32_t *flag, cudaStream_t st);
+// the rows listed in list[0 .. *count) only (the knn engine's tie rows); *count is added to *total
+int launch_knn_marked(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                      const int32_t *list, const int *count, unsigned long long *total, cudaStream_t st);
 int launch_svc_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
                      int32_t *flag, cudaStream_t st);
 int launch_ovr_from_ovo(const double *dec, int64_t n, int C, double *out, cudaStream_t st);

@@ -12,9 +12,22 @@
 // pieces of ||t||^2 against 1.0, and A is pre-scaled by -2, so that ONE tcgen05.mma chain of K = 80 yields
 //   acc(x,t) = ||t||^2 - 2 x.t      in fp32, to 2^-21 (||x||^2 + ||t||^2)   (all-pairs audit, tests/test_engine_gpu.py)
 // KNN only uses acc as a FILTER: a candidate is re-evaluated exactly (fp64, sklearn's summation order) iff
-// acc <= (worst kept distance - ||x||^2) + kappa (||x||^2 + ||t||^2), kappa = 2^-18; every row the sequential heap
-// would accept passes, every row that passes goes through the same heap_push in index order -> neighbours
-// identical to knn.cu / sklearn.  (The kappa ||t||^2 part is folded into the packed norm: B carries (1-kappa)||t||^2.)
+// acc <= (worst kept distance - ||x||^2) + kappa (||x||^2 + ||t||^2), kappa = 2^-18; every row that could enter the k-slot heap
+// passes, and every row that passes is offered to the heap with its exact distance.  (The kappa ||t||^2 part is folded into the
+// packed norm: B carries (1-kappa)||t||^2.)
+// KNN: spatial order and pruning.  The training rows are stored in kd order (create(): recursive median splits down to tiles
+// of 64), so a tile is a small ball (centre c_t, radius r_t).  A call first sorts its queries by HOME tile (the kd leaf a
+// query falls into: knn_key_kernel + a counting sort), so the 512 rows of a pass are neighbours too.  Per pass the producer
+// walks the tiles by the distance of their centres from the pass's home tile and loads tile t only if
+//   (||x0 - c_t|| - r_t - rho)^2 <= H        x0 = first row of the pass, rho = max ||x - x0||, H = max current k-th distance^2
+// -- otherwise no row of t can be among the k nearest of any row of the pass (triangle inequality; all roundings taken in the
+// safe direction; H only falls, so a stale H is merely less sharp).  The epilogue repeats the test per lane with its own
+// ||x - x0|| and k-th distance and skips the TMEM read and the filter when no lane of the warp needs the tile.  On the bench
+// workload (10M queries x 50k rows, k = 5) a pass multiplies ~1/6 of the tiles.
+// Order independence.  The k smallest distances are the same SET whatever the visiting order, except when rows tie at the
+// k-th distance: there sklearn's answer depends on its heap's history.  The epilogue watches for rows left out at exactly the
+// final k-th distance; if such a row and the kept rows at that distance do not all carry one class, the query goes to the
+// index-order fp64 kernel (knn.cu, marked mode) in the same call; otherwise every choice gives the same class counts.
 // SVC uses acc directly, for LABELS only: e = -gamma log2(e) (acc + ||x' - c'_j||^2), K = ex2(e), C-1 fp32 FMAs per pair into
 // the running sums of the support vector's class, tile sums promoted to fp64.  To keep the fp32 accumulation error small
 // where K is not negligible, support vectors are re-ordered inside their class into spatially compact tiles and every tile
@@ -49,8 +62,10 @@
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
 // followed (SVC) by the tile's dual coefficients [C-1][64] fp32, its centre c'_j and the two constants of eta_j.  A tile image is contiguous in HBM, so
 // one cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
-// boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows (even row
-// stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.
+// boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows in tile order
+// (even row stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.  Pruning tables:
+// tile centres and radii (fp64), the kd tree, and per home tile the list of all tiles by centre distance (n_tiles^2 x 2 B,
+// 1.2 MB at 782 tiles; models beyond 4096 tiles visit every tile).
 //
 // Kernel (persistent, 1 CTA / SM).  A CTA owns 512 query rows at a time:
 //   KNN: warps 0-15, each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
@@ -77,6 +92,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -107,6 +123,7 @@ constexpr float kKappa = 1.0f / 262144.0f;  // 2^-18: filter slack per unit of (
                                             // all-pairs audit observes (2^-21.0 .. 2^-20.4, tests/test_engine_gpu.py)
 constexpr int kEListCap = 24;               // per-thread candidate list, 16-bit entries (tile offset, group of 8 columns, mask)
 constexpr int kEListRoom = 8;               // one tile appends at most this many: lists are evaluated beyond cap - room
+constexpr int kEMaxPruneTiles = 4096;        // KNN: the tile-by-tile neighbour table is n_tiles^2 x 2 bytes; larger models visit every tile
 constexpr int kEFlushTiles = 31;            // default number of reference tiles between two evaluation rounds (KNN), <= 31
 
 struct EngineState {
@@ -117,7 +134,20 @@ struct EngineState {
     double *d_center = nullptr;         // [d]
     double *d_refpad = nullptr;         // KNN: original fp64 reference rows, row stride padded to an even count (16 B loads)
     float *d_maxratio = nullptr;        // audit: max observed |acc - exact| / (||x||^2 + ||t||^2)  (SVC: / M_j)
-    unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN) / rows handed to the fp64 kernel (SVC)
+    unsigned long long *d_counters = nullptr;  // [0] exact re-evaluations (KNN) / rows handed to the fp64 kernel (SVC),
+                                               // [1] KNN rows re-run in index order (class-relevant tie at the k-th distance),
+                                               // [2] KNN reference tiles multiplied (summed over passes), [3] KNN passes
+    // KNN pruning (see "KNN: spatial order and pruning" in the file header)
+    int32_t *d_kd_dim = nullptr;        // kd tree over the training rows: split coordinate per node, -1 = leaf
+    int32_t *d_kd_child = nullptr;      // [node][2]: children; a leaf keeps its tile in [node][0]
+    double *d_kd_split = nullptr;       // split value (rows with x[dim] < split go left)
+    double *d_tcent = nullptr;          // [n_tiles][d] tile centres
+    double *d_trad = nullptr;           // [n_tiles] tile radii (max distance of a row from the centre, rounded up)
+    uint16_t *d_nbr = nullptr;          // [n_tiles][n_tiles]: per home tile, all tiles by centre distance (nullptr: pruning off)
+    float *d_chunk_lb = nullptr;        // [n_tiles][n_chunks]: min over positions >= 32 c of (centre distance - radius)
+    int32_t *d_ypos = nullptr;          // training labels in tile order
+    float *d_tile_tn = nullptr;         // per tile: largest ||t - c0||^2 of its rows (rounded up)
+    cudaMemPool_t pool = nullptr;       // per-call scratch (query keys, permutation, tie list): stream-ordered allocations
     int n_tiles = 0;
     int tile_bytes = 0;
     int nc1 = 0;
@@ -133,7 +163,17 @@ struct EngineArgs {
     const double *center;
     const double *ref;       // original fp64 reference rows (audit statistic)
     const double *refpad;    // the same rows at a 16-byte-aligned stride of dpad doubles (KNN exact re-evaluation)
-    const int32_t *y;        // KNN labels
+    const int32_t *y;        // KNN labels (original order; unused by the engine since the tiles are in kd order)
+    const int32_t *ypos;     // KNN labels in tile order
+    const int32_t *qperm;    // KNN: this call's query order (sorted by home tile) or nullptr = as given
+    const int32_t *qkey;     // KNN: home tile per query (by original index)
+    const double *tcent;     // KNN: tile centres / radii
+    const double *trad;
+    const uint16_t *nbr;     // KNN: tiles by centre distance per home tile; nullptr = visit every tile in order, skip nothing
+    const float *chunk_lb;
+    const float *tile_tn;    // KNN: per tile, the largest centred squared norm of its rows
+    int32_t *tie_list;       // KNN: rows whose label needs the index-order heap (ties at the k-th distance across classes)
+    int *tie_count;
     const double *rho;       // SVC
     float *maxratio;         // non-null = audit mode
     int32_t *flag;
@@ -254,6 +294,29 @@ __device__ __forceinline__ void e_tmem_ld16_wait(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ int2 e_lds_v2(const void *p) {   // one 8-byte volatile shared load
+    int2 r;
+    asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(e_smem(p)) : "memory");
+    return r;
+}
+__device__ __forceinline__ void e_sts_v2(void *p, int2 v) {
+    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(e_smem(p)), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// one padded fp64 row (12 doubles, 16-byte aligned) through the read-only path: six 16-byte loads issued back to back
+__device__ __forceinline__ void e_ldg_row12(const double *p, double (&v)[12]) {
+    asm volatile(
+        "ld.global.nc.v2.f64 {%0, %1}, [%12];\n\t"
+        "ld.global.nc.v2.f64 {%2, %3}, [%12+16];\n\t"
+        "ld.global.nc.v2.f64 {%4, %5}, [%12+32];\n\t"
+        "ld.global.nc.v2.f64 {%6, %7}, [%12+48];\n\t"
+        "ld.global.nc.v2.f64 {%8, %9}, [%12+64];\n\t"
+        "ld.global.nc.v2.f64 {%10, %11}, [%12+80];"
+        : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]), "=d"(v[8]), "=d"(v[9]),
+          "=d"(v[10]), "=d"(v[11])
+        : "l"(p));
+}
+
 __device__ __forceinline__ float e_ex2(float x) {   // one MUFU.EX2 (2 ulp), flushes denormals
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -317,6 +380,68 @@ __device__ __forceinline__ void knn_heap_push(double *values, int32_t *indices, 
 __device__ __forceinline__ float knn_thr_base(double hv0, double qn) {
     if (hv0 >= 1e300) return FLT_MAX;
     return __double2float_ru((hv0 - qn) + (double)kKappa * qn);
+}
+
+// ------------------------------------------------------------------------------------------------ KNN: query order
+// The queries of a call are grouped by HOME tile (the kd leaf they fall into) so that the 512 rows of a pass are neighbours:
+// a counting sort in three kernels.  Block b owns the rows [b R, (b+1) R) in both passes over the rows.
+constexpr int kSortThreads = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kSortThreads) knn_key_kernel(const T *__restrict__ X, int64_t n, int d, int64_t rows_per_block,
+                                                               const int32_t *__restrict__ kd_dim, const int32_t *__restrict__ kd_child,
+                                                               const double *__restrict__ kd_split, int n_bins,
+                                                               int32_t *__restrict__ key, int32_t *__restrict__ block_hist) {
+    extern __shared__ int32_t s_hist[];
+    for (int i = threadIdx.x; i < n_bins; i += kSortThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * rows_per_block, hi = min(n, lo + rows_per_block);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kSortThreads) {
+        int node = 0, dim;
+        while ((dim = kd_dim[node]) >= 0)
+            node = kd_child[2 * node + (static_cast<double>(X[i * d + dim]) < kd_split[node] ? 0 : 1)];
+        const int tile = kd_child[2 * node];
+        key[i] = tile;
+        atomicAdd(&s_hist[tile], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bins; i += kSortThreads) block_hist[(size_t)blockIdx.x * n_bins + i] = s_hist[i];
+}
+
+// block_hist[b][bin] -> rows of that bin in the blocks before b; bin_start[bin] = rows in the bins before it
+__global__ void __launch_bounds__(1024) knn_scan_kernel(int32_t *__restrict__ block_hist, int n_blocks, int n_bins,
+                                                        int32_t *__restrict__ bin_start) {
+    extern __shared__ int32_t s_tot[];   // [n_bins]
+    for (int bin = threadIdx.x; bin < n_bins; bin += 1024) {
+        int run = 0;
+        for (int b0 = 0; b0 < n_blocks; b0 += 8) {   // eight loads in flight, then the eight stores
+            int c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) c[u] = b0 + u < n_blocks ? block_hist[(size_t)(b0 + u) * n_bins + bin] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (b0 + u < n_blocks) block_hist[(size_t)(b0 + u) * n_bins + bin] = run;
+                run += c[u];
+            }
+        }
+        s_tot[bin] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int bin = 0; bin < n_bins; ++bin) { const int c = s_tot[bin]; bin_start[bin] = run; run += c; }
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) knn_scatter_kernel(const int32_t *__restrict__ key, int64_t n, int64_t rows_per_block,
+                                                                   const int32_t *__restrict__ block_base,
+                                                                   const int32_t *__restrict__ bin_start, int n_bins,
+                                                                   int32_t *__restrict__ perm) {
+    extern __shared__ int32_t s_cur[];
+    for (int i = threadIdx.x; i < n_bins; i += kSortThreads) s_cur[i] = block_base[(size_t)blockIdx.x * n_bins + i] + bin_start[i];
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * rows_per_block, hi = min(n, lo + rows_per_block);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kSortThreads) perm[atomicAdd(&s_cur[key[i]], 1)] = (int32_t)i;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -386,6 +511,32 @@ __device__ __forceinline__ double e_pack_row(const EngineArgs &A, const T *__res
     return qn;
 }
 
+// experiment build (-DTCSDN_EXP_KNN_TIMING, tools/ only): cycles spent per role and phase, summed into counters[8 ..]
+#if defined(TCSDN_EXP_KNN_TIMING)
+#define KT_DECL long long kt_t0 = 0; long long kt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define KT_START() kt_t0 = clock64()
+#define KT_STOP(i) kt_acc[i] += clock64() - kt_t0
+#define KT_FLUSH(base, cond) if (cond) { for (int kt_i = 0; kt_i < 8; ++kt_i) atomicAdd(counters + 8 + (base) + kt_i, (unsigned long long)kt_acc[kt_i]); }
+#else
+#define KT_DECL
+#define KT_START()
+#define KT_STOP(i)
+#define KT_FLUSH(base, cond)
+#endif
+
+// KNN: what the producer, the MMA warp and the epilogue warps tell each other about the tiles of a pass
+constexpr int kEBarRegion = 3072;   // barriers (256 B) + KnnShared
+struct KnnShared {
+    int2 stageInfo[kEStages];        // producer -> MMA warp: (tile in the stage or -1 = end of pass, bits of its gap)
+    int2 accInfo[2];                 // MMA warp -> epilogue warps: the same for the accumulator buffer
+    float warpH[kEKnnWarps];         // per epilogue warp: largest k-th distance^2 among its rows (rounded up), +inf at pass start
+    unsigned rho_bits[2];            // by pass parity: largest distance of a row of the pass from the pass's first row (float bits)
+    int chunkT[32];                  // producer scratch: the 32 tiles of a chunk and their gaps
+    float chunkGap[32];
+    int32_t seqTile[kEKnnWarps][32];    // per epilogue warp: tile visited at each sequence position since the last round
+};
+static_assert(sizeof(KnnShared) + 256 <= kEBarRegion, "KnnShared does not fit");
+
 // AUDIT (SVC; KNN keeps its audit flag in NC1): a separate instantiation, because the audit indexes the accumulator registers
 // and x' dynamically, which would put them in local memory in the production kernel too
 template <typename T, bool SVC, int NC1, bool AUDIT = false>
@@ -403,7 +554,8 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(coefFree + kEStages);
     // after the barriers -- KNN: [512 threads][kEListCap] candidate lists, then the heaps; SVC: [P][512] fp64 pair sums,
     // then [P][512] fp32 error bounds
-    unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + 256;
+    unsigned char *cand = reinterpret_cast<unsigned char *>(bars) + kEBarRegion;
+    KnnShared *ks = reinterpret_cast<KnnShared *>(reinterpret_cast<unsigned char *>(bars) + 256);   // KNN only
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_super = (A.n + kERows - 1) / kERows;
@@ -419,6 +571,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
             e_mbar_init(&accEmpty[b], kEpi);
         }
         e_mbar_init(aFull, kEpi);
+        if constexpr (!SVC) { ks->rho_bits[0] = 0u; ks->rho_bits[1] = 0u; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpi + 1) {
@@ -432,17 +585,126 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
 
     if (warp == kEpi) {
         // ------------------------------------------------------------------ reference tile producer
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
-                for (int j = 0; j < A.n_tiles; ++j, ++g) {
-                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
-                    e_mbar_wait(&emptyB[s], ph ^ 1);
-                    if (SVC) e_mbar_wait(&coefFree[s], ph ^ 1);   // the epilogue warps are done with the stage's coefficients
-                    e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
-                    e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)j * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
+        if constexpr (SVC) {
+            if (lane == 0) {
+                uint32_t g = 0;
+                for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+                    for (int j = 0; j < A.n_tiles; ++j, ++g) {
+                        const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                        e_mbar_wait(&emptyB[s], ph ^ 1);
+                        e_mbar_wait(&coefFree[s], ph ^ 1);   // the epilogue warps are done with the stage's coefficients
+                        e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
+                        e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)j * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
+                    }
                 }
             }
+        } else {
+            // KNN: per pass, the tiles in the order of their centres' distance from the pass's home tile, each tested against
+            //   (||x0 - c_t|| - r_t - rho)^2 > H   =>  no row of tile t can enter the neighbour set of any row of the pass
+            // (x0 = first row of the pass, rho = largest ||x - x0|| in the pass, H = largest current k-th distance^2 in the pass;
+            // H only falls, so a test that passes with a stale H stays valid).  Lanes compute the 32 gaps of a chunk in fp64, lane 0
+            // walks the chunk with the current H and loads what survives; a chunk-level bound ends the pass early.
+            const bool prune = A.nbr != nullptr && A.qperm != nullptr;
+            const int n_chunks = (A.n_tiles + 31) >> 5;
+            uint32_t g = 0, pass = 0;            // g is lane 0's
+            unsigned long long n_mult = 0;
+            KT_DECL;
+            for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
+                KT_START();
+                e_mbar_wait(aFull, pass & 1);    // the pass's rows are packed, rho is known
+                KT_STOP(0);
+                KT_START();
+                const int64_t src0 = A.qperm ? (int64_t)A.qperm[st * kERows] : st * kERows;
+                int home = 0;
+                float rho = 0.f, base_up = 0.f;
+                double x0[kEMaxD];
+                if (prune) {
+                    home = A.qkey[src0];
+                    rho = __uint_as_float(*reinterpret_cast<volatile unsigned *>(&ks->rho_bits[pass & 1]));
+                    double dh = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < kEMaxD; ++jj) {
+                        x0[jj] = jj < A.d ? static_cast<double>(X[src0 * A.d + jj]) : 0.0;
+                        const double df = jj < A.d ? x0[jj] - A.tcent[(size_t)home * A.d + jj] : 0.0;
+                        dh += df * df;
+                    }
+                    base_up = __fadd_ru(__double2float_ru(sqrt(dh) * (1.0 + 1e-12)), rho);   // >= ||q - c_home|| for every row q of the pass
+                }
+                auto current_h = [&]() {         // every lane: max over the epilogue warps
+                    float h = lane < kEKnnWarps ? *reinterpret_cast<volatile float *>(&ks->warpH[lane]) : 0.f;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+                    return h;
+                };
+                KT_STOP(1);
+                for (int c = 0; c < n_chunks; ++c) {
+                    KT_START();
+                    const float current_h_all = prune ? current_h() : 0.f;
+                    if (prune) {                 // everything from this chunk on is farther than H from every row of the pass
+                        const float mgn = __fsub_rd(A.chunk_lb[(size_t)home * n_chunks + c], base_up);
+                        if (mgn > 0.f && __fmul_rd(mgn, mgn) > current_h_all) break;
+                    }
+                    int t = c * 32 + lane;
+                    const bool valid = t < A.n_tiles;
+                    float gap = -FLT_MAX;
+                    if (prune && valid) {
+                        t = A.nbr[(size_t)home * A.n_tiles + t];
+                        double dd = 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < kEMaxD; ++jj) {
+                            const double df = jj < A.d ? x0[jj] - A.tcent[(size_t)t * A.d + jj] : 0.0;
+                            dd += df * df;
+                        }
+                        gap = __double2float_rd(sqrt(dd) * (1.0 - 1e-12) - A.trad[t]);   // <= ||x0 - row|| for every row of tile t
+                    }
+                    // every lane tests its own tile against the H of this moment; lane 0 then walks the survivors in order and
+                    // tests each once more with the H of the moment it is loaded
+                    bool keep = valid;
+                    if (prune && valid) {
+                        const float mgn = __fsub_rd(gap, rho);
+                        keep = !(mgn > 0.f && __fmul_rd(mgn, mgn) > current_h_all);
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, keep);
+                    ks->chunkT[lane] = t;
+                    ks->chunkGap[lane] = gap;
+                    __syncwarp();
+                    KT_STOP(2);
+                    if (lane == 0) {
+                        for (; todo; todo &= todo - 1) {
+                            const int i = __ffs(todo) - 1;
+                            const int ti = ks->chunkT[i];
+                            const float gi = ks->chunkGap[i];
+                            if (prune) {
+                                float h = 0.f;
+#pragma unroll
+                                for (int w = 0; w < kEKnnWarps; ++w) h = fmaxf(h, *reinterpret_cast<volatile float *>(&ks->warpH[w]));
+                                const float mgn = __fsub_rd(gi, rho);
+                                if (mgn > 0.f && __fmul_rd(mgn, mgn) > h) continue;
+                            }
+                            const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                            KT_START();
+                            e_mbar_wait(&emptyB[s], ph ^ 1);
+                            KT_STOP(3);
+                            e_sts_v2(&ks->stageInfo[s], make_int2(ti, __float_as_int(gi)));
+                            e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
+                            e_bulk_g2s(sB + (size_t)s * A.tile_bytes, A.tiles + (size_t)ti * A.tile_bytes, (uint32_t)A.tile_bytes, &fullB[s]);
+                            ++g;
+                            ++n_mult;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {                 // end of pass: an empty stage that carries -1
+                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                    e_mbar_wait(&emptyB[s], ph ^ 1);
+                    e_sts_v2(&ks->stageInfo[s], make_int2(-1, 0));
+                    e_mbar_arrive(&fullB[s]);
+                    ++g;
+                }
+                __syncwarp();
+            }
+            if (lane == 0 && counters) { atomicAdd(counters + 2, n_mult); atomicAdd(counters + 3, (unsigned long long)pass); }
+            KT_FLUSH(0, lane == 0 && counters);
         }
     } else if (warp == kEpi + 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -457,64 +719,110 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
         const uint64_t desc_hi = ((uint64_t)(kESBO >> 4) | ((uint64_t)1 << 14)) << 32;
         const uint32_t a_lo = ((e_smem(sA) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
         uint32_t g = 0, pass = 0;
+        KT_DECL;
         for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
+            KT_START();
             e_mbar_wait(aFull, pass & 1);   // the 512 query rows of this pass are packed
+            KT_STOP(0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int j = 0; j < A.n_tiles; ++j, ++g) {
+            // SVC: every tile, in order.  KNN: whatever the producer sends, until the stage that carries -1
+            for (int j = 0; SVC ? j < A.n_tiles : true; ++j, ++g) {
                 const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
                 const uint32_t b = g & 1, bph = (g >> 1) & 1;
+                KT_START();
                 e_mbar_wait(&fullB[s], ph);
+                KT_STOP(1);
+                int2 info = make_int2(0, 0);
+                if constexpr (!SVC) info = e_lds_v2(&ks->stageInfo[s]);
+                const bool last = !SVC && info.x < 0;
+                KT_START();
                 e_mbar_wait(&accEmpty[b], bph ^ 1);
+                KT_STOP(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (e_elect_one()) {
-                    const uint32_t b_lo = ((e_smem(sB + (size_t)s * A.tile_bytes) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+                    if constexpr (!SVC) e_sts_v2(&ks->accInfo[b], info);
+                    if (!last) {
+                        const uint32_t b_lo = ((e_smem(sB + (size_t)s * A.tile_bytes) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
+                        for (int t = 0; t < 4; ++t) {
+                            const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
 #pragma unroll
 #if defined(TCSDN_EXP_NO_MMA)     // experiment build: no MMA at all (commits only)
-                        for (int k = 0; k < 0; ++k)
+                            for (int k = 0; k < 0; ++k)
 #elif defined(TCSDN_EXP_ONE_MMA)  // experiment build: one K step instead of five (a fifth of the operand reads)
-                        for (int k = 0; k < 1; ++k)
+                            for (int k = 0; k < 1; ++k)
 #else
-                        for (int k = 0; k < kEKSteps; ++k)
+                            for (int k = 0; k < kEKSteps; ++k)
 #endif
-                            e_mma(dcol, desc_hi | (uint64_t)(a_lo + (uint32_t)(t * (kEATile >> 4) + k * 16)),
-                                  desc_hi | (uint64_t)(b_lo + (uint32_t)(k * 16)), idesc, k > 0);
+                                e_mma(dcol, desc_hi | (uint64_t)(a_lo + (uint32_t)(t * (kEATile >> 4) + k * 16)),
+                                      desc_hi | (uint64_t)(b_lo + (uint32_t)(k * 16)), idesc, k > 0);
+                        }
+                        e_commit(&emptyB[s]);    // smem stage may be refilled once these MMAs have read it
+                    } else {
+                        e_mbar_arrive(&emptyB[s]);   // nothing reads the end-of-pass stage
                     }
-                    e_commit(&emptyB[s]);    // smem stage may be refilled once these MMAs have read it
-                    e_commit(&accFull[b]);   // accumulators of this reference tile are complete
+                    e_commit(&accFull[b]);   // accumulators of this reference tile are complete (end of pass: nothing pending)
                 }
                 __syncwarp();
+                if (last) { ++g; break; }
             }
         }
+        KT_FLUSH(8, !SVC && lane == 0 && counters);
     } else if constexpr (!SVC) {
         // ------------------------------------------------------------------ KNN: 512 query-row owners (pack A, filter epilogue)
         const int qt = warp >> 2;                           // query tile 0..3
         const int rt = (warp & 3) * 32 + lane;              // row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        uint32_t g = 0;
+        const bool prune = A.nbr != nullptr && A.qperm != nullptr;
+        uint32_t g = 0, pass = 0;
         float nf = 0.f;
-        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
-            const int64_t row = st * kERows + qt * 128 + rt;
-            const bool live = row < A.n;
+        KT_DECL;
+        for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
+            KT_START();
+            const int64_t slot = st * kERows + qt * 128 + rt;
+            const bool live = slot < A.n;
+            const int64_t row = !live ? 0 : (A.qperm ? (int64_t)A.qperm[slot] : slot);   // the query this thread owns
             float xp_unused[kEMaxD];
             const double qn = e_pack_row<T, false>(A, X, row, live, sA, qt, rt, nf, xp_unused);
+            // distance from the pass's first row (the producer's reference point), rounded up; its maximum over the pass is rho
+            float e_up = 0.f;
+            if (prune) {
+                const int64_t src0 = (int64_t)A.qperm[st * kERows];
+                double e2 = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < kEMaxD; ++jj)
+                    if (jj < A.d && live) {
+                        const double df = static_cast<double>(X[row * A.d + jj]) - static_cast<double>(X[src0 * A.d + jj]);
+                        e2 += df * df;
+                    }
+                e_up = __double2float_ru(sqrt(e2) * (1.0 + 1e-12));
+                if (!(e_up >= 0.f)) e_up = FLT_MAX;          // non-finite row: never skip on its behalf (the call fails anyway)
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(e_up));
+                if (lane == 0) {
+                    atomicMax(&ks->rho_bits[pass & 1], wmax);
+                    *reinterpret_cast<volatile float *>(&ks->warpH[warp]) = __int_as_float(0x7f800000);
+                }
+                if (tid == 0) ks->rho_bits[(pass + 1) & 1] = 0u;   // the other parity's slot is idle during this pass
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
             __syncwarp();
             if (lane == 0) e_mbar_arrive(aFull);
+            KT_STOP(0);
 
             {
                 // ================================================================ KNN: filter, deferred exact heap
                 // acc = (1 - kappa) ||t||^2 - 2 x.t, so a row passes iff acc <= thr = (worst kept distance - ||x||^2)
-                // + kappa ||x||^2.  Passing columns are appended to a per-thread list (tile offset << 6 | column) and the
-                // lists are evaluated every `flush_tiles` tiles (or when one runs full): exact fp64 distance in sklearn's
-                // rdist order from the original rows (L2-resident), then heap_push -- per query still in training-index
-                // order, so the heap is the sequential one.  Deferral only makes the threshold staler, i.e. the filter a
-                // little more permissive; what it buys is warp efficiency: evaluating right after every tile kept ~5 of 32
-                // lanes busy (most lanes have no candidate in a given tile), batching 16 tiles keeps about half of them busy,
-                // and all 16 warps evaluate at the same tile indices instead of stalling each other through the two
-                // accumulator buffers.
+                // + kappa ||x||^2.  Passing columns are appended to a per-thread list (sequence offset, group of 8 columns, pass
+                // mask) and the lists are evaluated every `flush_tiles` tiles (or when one runs full): exact fp64 distance in
+                // sklearn's rdist order from the original rows (L2-resident), then heap_push.  Deferral only makes the
+                // threshold staler, i.e. the filter a little more permissive; what it buys is warp efficiency.
+                // ORDER.  The tiles arrive in the producer's order (nearest first), not in training-index order.  The k smallest
+                // distances are the same set whatever the order unless rows TIE at the k-th distance; there sklearn's answer
+                // depends on its heap's history (which of the equal entries sits at the root when a smaller one arrives).  The
+                // kernel therefore watches for rows left out at exactly the final k-th distance (rejected at the root's value,
+                // or evicted while an equal value stays): if such a row and the kept rows at that distance do not all carry one
+                // class, the label depends on the choice and the row goes to the index-order fp64 kernel (tie_list); otherwise
+                // the class counts -- label and probabilities -- are the same for every choice.
                 // The k-slot max-heap: shared memory [slot][thread] for k <= 8 (NC1 bit 0), else thread-private local
                 // memory.  Its root and the filter threshold stay in registers.
                 constexpr bool kHeapSmem = (NC1 & 1) != 0;      // KNN instantiations: NC1 bit 0 = heap in shared memory,
@@ -526,27 +834,45 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                 double *hv = kHeapSmem ? reinterpret_cast<double *>(heap_base) + tid : hv_local;
                 int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(heap_base + 512 * (size_t)A.k * sizeof(double)) + tid : hi_local;
                 for (int i = 0; i < A.k; ++i) { hv[i * ST] = DBL_MAX; hi[i * ST] = 0; }
-                double hv0 = DBL_MAX;
-                float thr_base = FLT_MAX;
+                double hv0 = DBL_MAX, tie_val = -1.0;
+                int tie_cls = -1;
+                float thr_base = FLT_MAX, hv0f = __int_as_float(0x7f800000);
                 unsigned long long n_exact = 0;
-                // candidate list entries: tile offset since the last round << 11 | group of 8 columns << 8 | pass mask
+                // candidate list entries: sequence offset since the last round << 11 | group of 8 columns << 8 | pass mask
                 uint16_t *mylist = reinterpret_cast<uint16_t *>(cand) + (size_t)tid * kEListCap;
-                int cnt = 0, base_tile = 0, next_round = 1;
+                int32_t *myseq = ks->seqTile[warp];
+                int cnt = 0, base_seq = 0, next_round = 1, j = 0;
+                bool end = false;
                 const uint32_t taddr0 = tmem_base + lane_addr + (uint32_t)(qt * 2 * kEN);
+                auto tie_note = [&](double v, int32_t pos) {   // a row left out of the heap at the root's value v
+                    const int c = A.ypos[pos];
+                    if (v != tie_val) { tie_val = v; tie_cls = c; }
+                    else if (tie_cls != c) tie_cls = -2;
+                };
+                auto offer = [&](double dv, int32_t pos) {
+                    if (dv < hv0) {
+                        const double ev = hv0;
+                        const int32_t ei = hi[0];
+                        knn_heap_push<ST>(hv, hi, A.k, dv, pos);
+                        hv0 = hv[0];
+                        if (hv0 == ev) tie_note(ev, ei);      // the evicted row is as far as the new root
+                    } else if (dv == hv0) tie_note(dv, pos);
+                };
 #pragma unroll 1
-                for (int j = 0; j <= A.n_tiles; ++j) {
+                for (;;) {
                     // ---- evaluation round: at the end, every `period` tiles (short while the threshold is still falling
                     // fast), or when a list could overflow in this tile
-                    const bool need = j >= next_round || cnt > kEListCap - kEListRoom;
+                    const bool need = end || j >= next_round || cnt > kEListCap - kEListRoom;
                     if (__any_sync(0xffffffffu, need)) {
+                        KT_START();
                         int li = 0, gbase = 0;
                         uint32_t m = 0;
-                        auto next = [&](int32_t &idx) -> bool {   // pops this thread's next candidate (training index order)
+                        auto next = [&](int32_t &idx) -> bool {   // pops this thread's next candidate (position in tile order)
                             if (m == 0) {
                                 if (li >= cnt) return false;
                                 const uint32_t e = mylist[li++];
                                 m = e & 255u;
-                                gbase = ((base_tile + (int)(e >> 11)) << 6) + (int)((e >> 8) & 7u) * 8;
+                                gbase = (myseq[e >> 11] << 6) + (int)((e >> 8) & 7u) * 8;
                             }
                             idx = gbase + __ffs(m) - 1;
                             m &= m - 1;
@@ -563,44 +889,68 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                             const bool pa = next(ia);
                             const bool pb = pa && next(ib);
                             if (!__any_sync(0xffffffffu, pa)) break;
-                            const double2 *ta = reinterpret_cast<const double2 *>(A.refpad + (size_t)ia * A.dpad);
-                            const double2 *tb = reinterpret_cast<const double2 *>(A.refpad + (size_t)ib * A.dpad);
+                            // all twelve 16-byte loads first (ONE L2 round trip for both rows: single asm blocks, so that the
+                            // compiler cannot spread them between the uses), then the two fp64 chains.  Rows are padded to 12
+                            // doubles with zeros and x is zero there too: the extra terms add +0.0, the sums are unchanged.
+                            double va[kEMaxD], vb[kEMaxD];
+                            e_ldg_row12(A.refpad + (size_t)ia * kEMaxD, va);
+                            e_ldg_row12(A.refpad + (size_t)ib * kEMaxD, vb);
                             double da = 0.0, db = 0.0;
 #pragma unroll
-                            for (int jj = 0; jj < kEMaxD; jj += 2)
-                                if (jj < A.d) {
-                                    const double2 va = __ldg(ta + (jj >> 1)), vb = __ldg(tb + (jj >> 1));
-                                    const double q0 = static_cast<double>(qx[jj]);
-                                    double df = __dsub_rn(q0, va.x);
-                                    da = __dadd_rn(da, __dmul_rn(df, df));
-                                    df = __dsub_rn(q0, vb.x);
-                                    db = __dadd_rn(db, __dmul_rn(df, df));
-                                    if (jj + 1 < A.d) {
-                                        const double q1 = static_cast<double>(qx[jj + 1]);
-                                        df = __dsub_rn(q1, va.y);
-                                        da = __dadd_rn(da, __dmul_rn(df, df));
-                                        df = __dsub_rn(q1, vb.y);
-                                        db = __dadd_rn(db, __dmul_rn(df, df));
-                                    }
-                                }
+                            for (int jj = 0; jj < kEMaxD; ++jj) {
+                                const double q0 = static_cast<double>(qx[jj]);
+                                double df = __dsub_rn(q0, va[jj]);
+                                da = __dadd_rn(da, __dmul_rn(df, df));
+                                df = __dsub_rn(q0, vb[jj]);
+                                db = __dadd_rn(db, __dmul_rn(df, df));
+                            }
                             n_exact += (unsigned)pa + (unsigned)pb;
-                            if (pa && da < hv0) { knn_heap_push<ST>(hv, hi, A.k, da, ia); hv0 = hv[0]; }
-                            if (pb && db < hv0) { knn_heap_push<ST>(hv, hi, A.k, db, ib); hv0 = hv[0]; }
+                            if (pa) offer(da, ia);
+                            if (pb) offer(db, ib);
                         }
                         thr_base = knn_thr_base(hv0, qn);
+                        hv0f = __double2float_ru(hv0);
+                        if (prune) {      // tell the producer how far this warp's rows still look
+                            const unsigned hmax = __reduce_max_sync(0xffffffffu, live ? __float_as_uint(hv0f) : 0u);
+                            if (lane == 0) *reinterpret_cast<volatile float *>(&ks->warpH[warp]) = __uint_as_float(hmax);
+                        }
                         cnt = 0;
-                        base_tile = j;
-                        // next round: soon while the threshold is still falling fast, then every flush_tiles tiles
-                        next_round = min(A.n_tiles, j + min(A.flush_tiles, 1 + (j >> 2)));
+                        base_seq = j;
+                        // next round: after 1, 2, 4, 8, ... tiles while the threshold is still falling fast, then every flush_tiles tiles
+                        next_round = j + min(A.flush_tiles, max(1, j));
+                        KT_STOP(1);
                     }
-                    if (j == A.n_tiles) break;
-                    // ---- filter one reference tile: two halves of 32 accumulator columns (keeps 32, not 64, values live)
+                    if (end) break;
+                    // ---- the next tile of the pass (or its end)
                     const uint32_t b = g & 1, bph = (g >> 1) & 1;
                     ++g;
+                    KT_START();
                     e_mbar_wait(&accFull[b], bph);
+                    KT_STOP(2);
+                    KT_START();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const float thr = !live ? -FLT_MAX : (kAudit ? FLT_MAX : thr_base);
-                    const uint32_t etile = (uint32_t)(j - base_tile) << 11;
+                    const int2 info = e_lds_v2(&ks->accInfo[b]);
+                    if (info.x < 0) {                       // end of pass (the branch on info also orders the load before the arrive)
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) e_mbar_arrive(&accEmpty[b]);
+                        end = true;
+                        continue;
+                    }
+                    // this row cannot gain a neighbour from the tile: ||x - t|| >= ||x0 - t|| - ||x - x0|| >= gap - e > sqrt(k-th distance^2)
+                    const float mgn = __fsub_rd(__int_as_float(info.y), e_up);
+                    const bool far = !live || (!kAudit && prune && mgn > 0.f && __fmul_rd(mgn, mgn) > hv0f);
+                    if (lane == 0) myseq[j - base_seq] = info.x;
+                    if (__all_sync(0xffffffffu, far)) {     // nobody in the warp needs the tile: release the buffer unread
+                        __syncwarp();
+                        if (lane == 0) e_mbar_arrive(&accEmpty[b]);
+                        ++j;
+                        KT_STOP(3);
+                        continue;
+                    }
+                    // ---- filter the tile: two halves of 32 accumulator columns (keeps 32, not 64, values live)
+                    float thr = far ? -FLT_MAX : (kAudit ? FLT_MAX : thr_base);
+                    const uint32_t etile = (uint32_t)(j - base_seq) << 11;
                     uint32_t lp = e_smem(mylist) + 2u * (uint32_t)cnt;   // 32-bit shared address of the list's tail
                     // all 64 accumulator values go to registers at once and the TMEM buffer is released right away: what a
                     // warp then does with them (group visits, an evaluation round) no longer holds up the next tile's MMAs
@@ -613,6 +963,38 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) e_mbar_arrive(&accEmpty[b]);   // TMEM buffer may be overwritten
+                    if constexpr (kHeapSmem && !kAudit) {
+                        // No threshold yet (the pass's first tile): instead of re-evaluating all 64 rows exactly, take the k-th
+                        // smallest ACCUMULATOR value s: the k-th smallest exact distance of the tile is at most
+                        //   U = s + ||x||^2 + 2 kappa (||x||^2 + TN)      (TN = the tile's largest ||t||^2; |acc - (d - ||x||^2 -
+                        //   kappa ||t||^2)| <= kappa/4 (||x||^2 + ||t||^2) is what the all-pairs audit bounds)
+                        // and filtering with U in the place of the heap's root keeps every row that can be among the k nearest.
+                        if (thr == FLT_MAX) {
+                            float s8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) s8[i] = __int_as_float(0x7f800000);
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) {
+                                const float vv = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+                                if (vv < s8[7]) {
+                                    s8[7] = vv;
+#pragma unroll
+                                    for (int q = 7; q > 0; --q) {
+                                        const float lo = fminf(s8[q - 1], s8[q]), hi2 = fmaxf(s8[q - 1], s8[q]);
+                                        s8[q - 1] = lo; s8[q] = hi2;
+                                    }
+                                }
+                            }
+                            float sk = s8[0];
+#pragma unroll
+                            for (int i = 1; i < 8; ++i) sk = (i == A.k - 1) ? s8[i] : sk;
+                            if (sk < FLT_MAX) {
+                                const float qnf = __double2float_ru(qn);
+                                const float slack = __fmul_ru(2.0f * kKappa, __fadd_ru(qnf, A.tile_tn[info.x]));
+                                thr = __fadd_ru(__fadd_ru(sk, slack), __fmul_ru(kKappa, qnf));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         float v[32];
@@ -639,9 +1021,9 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                             if constexpr (kAudit) {   // error statistic while the accumulator values are at hand
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
-                                    const int tr = j * kEN + h * 32 + gq * 8 + c;
-                                    if (((mask >> c) & 1u) && tr < A.n_ref) {
-                                        const double *t = A.ref + (size_t)tr * A.d;
+                                    const int col = h * 32 + gq * 8 + c;
+                                    if (((mask >> c) & 1u) && col < A.tile_rows[info.x]) {
+                                        const double *t = A.refpad + ((size_t)info.x * kEN + col) * A.dpad;
                                         double dist = 0.0, tn = 0.0;
                                         for (int jj = 0; jj < A.d; ++jj) {
                                             const double df = static_cast<double>(X[row * A.d + jj]) - t[jj], u = t[jj] - A.center[jj];
@@ -655,20 +1037,36 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                         }
                     }
                     cnt = (int)((lp - e_smem(mylist)) >> 1);
+                    ++j;
+                    KT_STOP(4);
                 }
+                KT_START();
                 if (live) {
-                    int best = 0, arg = 0;
-                    for (int c = 0; c < A.C; ++c) {
-                        int cnt = 0;
-                        for (int i = 0; i < A.k; ++i) cnt += (A.y[hi[i * ST]] == c);
-                        if (scores) scores[row * A.C + c] = (double)cnt / (double)A.k;
-                        if (cnt > best) { best = cnt; arg = c; }
+                    // a row outside the kept set at exactly the k-th distance: does the choice among the tied rows matter?
+                    bool tied = false;
+                    if (tie_val == hv0) {
+                        tied = tie_cls < 0;
+                        for (int i = 0; i < A.k; ++i) tied |= (hv[i * ST] == hv0 && A.ypos[hi[i * ST]] != tie_cls);
                     }
-                    labels[row] = arg;
+                    if (tied) {
+                        labels[row] = -1;
+                        A.tie_list[atomicAdd(A.tie_count, 1)] = (int32_t)row;
+                    } else {
+                        int best = 0, arg = 0;
+                        for (int c = 0; c < A.C; ++c) {
+                            int votes = 0;
+                            for (int i = 0; i < A.k; ++i) votes += (A.ypos[hi[i * ST]] == c);
+                            if (scores) scores[row * A.C + c] = (double)votes / (double)A.k;
+                            if (votes > best) { best = votes; arg = c; }
+                        }
+                        labels[row] = arg;
+                    }
                     if (counters) atomicAdd(counters, n_exact);
                 }
+                KT_STOP(5);
             }
         }
+        KT_FLUSH(16, lane == 0 && counters);
         if (A.flag && nf != nf) atomicOr(A.flag, 1);
     } else {
         // ------------------------------------------------------------------ SVC: 8 warps x 2 query rows per thread
@@ -1030,6 +1428,38 @@ static void compact_order(const std::vector<double> &ref, int d, std::vector<int
     compact_order(ref, d, idx, mid, hi);
 }
 
+// KNN: the same ordering, recorded as a tree.  Every leaf is exactly one tile (splits fall on tile boundaries); a query row
+// descends with `x[dim] < split ? left : right` to its HOME tile (knn_key_kernel).
+struct KdTree {
+    std::vector<int32_t> dim, child;
+    std::vector<double> split;
+};
+static int kd_build(const std::vector<double> &ref, int d, std::vector<int32_t> &idx, size_t lo, size_t hi, KdTree &kd) {
+    const int node = (int)kd.dim.size();
+    kd.dim.push_back(-1);
+    kd.child.push_back((int32_t)(lo / kEN));
+    kd.child.push_back(0);
+    kd.split.push_back(0.0);
+    if (hi - lo <= (size_t)kEN) return node;
+    int best = 0;
+    double bw = -1.0;
+    for (int j = 0; j < d; ++j) {
+        double mn = 1e300, mx = -1e300;
+        for (size_t i = lo; i < hi; ++i) { const double v = ref[(size_t)idx[i] * d + j]; mn = std::min(mn, v); mx = std::max(mx, v); }
+        if (mx - mn > bw) { bw = mx - mn; best = j; }
+    }
+    const size_t mid = lo + (((hi - lo) / 2 + kEN - 1) / kEN) * kEN;   // a tile boundary, lo < mid < hi because hi - lo > 64
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                     [&](int32_t a, int32_t b2) { return ref[(size_t)a * d + best] < ref[(size_t)b2 * d + best]; });
+    kd.dim[(size_t)node] = best;
+    kd.split[(size_t)node] = ref[(size_t)idx[mid] * d + best];
+    const int l = kd_build(ref, d, idx, lo, mid, kd);
+    const int r = kd_build(ref, d, idx, mid, hi, kd);
+    kd.child[2 * (size_t)node] = l;
+    kd.child[2 * (size_t)node + 1] = r;
+    return node;
+}
+
 // a padding row that is "infinitely" far from everything.  KNN: +inf, so that it fails the filter even while the
 // threshold is still FLT_MAX (A's norm slot is 1.0 and the row's other entries are 0: no 0 x inf).  SVC: 1e30, ex2 -> 0.
 static void pack_dummy(unsigned char *tile, int r, int d, bool inf) {
@@ -1062,14 +1492,16 @@ int engine_create(tcsdn_model *m) {
     E->nc1 = nc1;
     // tile image = bf16 B operand, then (SVC only) the tile's dual coefficients + centre
     E->tile_bytes = kETileB + (svc ? nc1 * kEN * (int)sizeof(float) + 16 * (int)sizeof(float) : 0);
-    // tile plan: KNN = consecutive rows in the original order (the heap semantics need index order);
+    // tile plan: KNN = kd order (spatially compact tiles: whole tiles can be skipped, see the file header);
     // SVC = per class (sums are per class), rows re-ordered inside the class for spatial compactness (sums do not
     // care about order), padded to a tile boundary with zero-coefficient rows
     std::vector<int32_t> row0, rows, tclass, order((size_t)nref);
     std::vector<double> coef;          // SVC: dual coefficients [nc1][nref]
     std::vector<uint8_t> pattern;      // SVC: per support vector, bit mm set iff coefficient row mm is non-zero
     for (int64_t i = 0; i < nref; ++i) order[(size_t)i] = (int32_t)i;
+    KdTree kd;
     if (!svc) {
+        kd_build(ref, d, order, 0, (size_t)nref, kd);
         for (int64_t r = 0; r < nref; r += kEN) { row0.push_back((int32_t)r); rows.push_back((int32_t)std::min<int64_t>(kEN, nref - r)); tclass.push_back(0); }
     } else {
         std::vector<int32_t> start(m->n_classes + 1);
@@ -1107,6 +1539,7 @@ int engine_create(tcsdn_model *m) {
     }
     E->n_tiles = (int)row0.size();
     std::vector<unsigned char> img((size_t)E->n_tiles * E->tile_bytes, 0);
+    std::vector<float> tile_tn((size_t)E->n_tiles, 0.f);
     for (int t = 0; t < E->n_tiles; ++t) {
         unsigned char *tile = img.data() + (size_t)t * E->tile_bytes;
         double tc[kEMaxD], delta[kEMaxD];
@@ -1146,6 +1579,7 @@ int engine_create(tcsdn_model *m) {
                 pack_dummy(tile, r, d, !svc);
             }
         }
+        tile_tn[(size_t)t] = std::nextafterf(static_cast<float>(rmax2), INFINITY);
         if (svc) {   // constants of eta_j (file header), rounded up
             const double rj = std::sqrt(rmax2) * (1.0 + 1e-6), cj = std::sqrt(cnorm) * (1.0 + 1e-6);
             const double eps = (double)kSvcEpsMma, p23 = 1.0 / 8388608.0;
@@ -1180,20 +1614,84 @@ int engine_create(tcsdn_model *m) {
             }
     }
     int rc = upload(&E->d_tiles, img.data(), img.size());
-    if (rc == TCSDN_OK && !svc) {   // exact re-evaluation reads the original rows with 16-byte loads: even row stride
-        const int dpad = (d + 1) & ~1;
-        std::vector<double> pad((size_t)nref * dpad, 0.0);
-        for (int64_t i = 0; i < nref; ++i) memcpy(&pad[(size_t)i * dpad], &ref[(size_t)i * d], (size_t)d * sizeof(double));
+    if (rc == TCSDN_OK && !svc) {
+        // exact re-evaluation reads the original rows with 16-byte loads: even row stride; rows in TILE order (a candidate is
+        // (tile, column)), labels likewise
+        const int dpad = kEMaxD;
+        const size_t npos = (size_t)E->n_tiles * kEN;
+        std::vector<double> pad(npos * dpad, 0.0);
+        std::vector<int32_t> ypos(npos, 0), yh((size_t)nref);
+        TCSDN_CUDA(cudaMemcpy(yh.data(), m->d_y, yh.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < nref; ++i) {
+            memcpy(&pad[(size_t)i * dpad], &ref[(size_t)order[(size_t)i] * d], (size_t)d * sizeof(double));
+            ypos[(size_t)i] = yh[(size_t)order[(size_t)i]];
+        }
         rc = upload(&E->d_refpad, pad.data(), pad.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_ypos, ypos.data(), ypos.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_tile_tn, tile_tn.data(), tile_tn.size());
+        // pruning tables: tile centres and radii, the kd tree, and per home tile the tiles by centre distance
+        const int nt = E->n_tiles;
+        std::vector<double> tcent((size_t)nt * d, 0.0), trad((size_t)nt, 0.0);
+        for (int t = 0; t < nt; ++t) {
+            for (int j = 0; j < d; ++j) {
+                double a = 0.0;
+                for (int r = 0; r < rows[t]; ++r) a += ref[(size_t)order[(size_t)(row0[t] + r)] * d + j];
+                tcent[(size_t)t * d + j] = a / rows[t];
+            }
+            double r2 = 0.0;
+            for (int r = 0; r < rows[t]; ++r) {
+                double a = 0.0;
+                for (int j = 0; j < d; ++j) { const double df = ref[(size_t)order[(size_t)(row0[t] + r)] * d + j] - tcent[(size_t)t * d + j]; a += df * df; }
+                r2 = std::max(r2, a);
+            }
+            trad[(size_t)t] = std::sqrt(r2) * (1.0 + 1e-9) + 1e-300;
+        }
+        if (rc == TCSDN_OK) rc = upload(&E->d_tcent, tcent.data(), tcent.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_trad, trad.data(), trad.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_kd_dim, kd.dim.data(), kd.dim.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_kd_child, kd.child.data(), kd.child.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_kd_split, kd.split.data(), kd.split.size());
+        if (rc == TCSDN_OK && nt <= kEMaxPruneTiles) {
+            const int nch = (nt + 31) / 32;
+            std::vector<uint16_t> nbr((size_t)nt * nt);
+            std::vector<float> clb((size_t)nt * nch);
+            std::vector<std::pair<double, int>> byd((size_t)nt);
+            for (int h = 0; h < nt; ++h) {
+                for (int t = 0; t < nt; ++t) {
+                    double a = 0.0;
+                    for (int j = 0; j < d; ++j) { const double df = tcent[(size_t)h * d + j] - tcent[(size_t)t * d + j]; a += df * df; }
+                    byd[(size_t)t] = {std::sqrt(a), t};
+                }
+                std::sort(byd.begin(), byd.end());
+                double suffix = 1e300;   // min over positions >= i of (centre distance - radius), rounded down
+                for (int i = nt - 1; i >= 0; --i) {
+                    nbr[(size_t)h * nt + i] = (uint16_t)byd[(size_t)i].second;
+                    suffix = std::min(suffix, byd[(size_t)i].first * (1.0 - 1e-9) - trad[(size_t)byd[(size_t)i].second]);
+                    if ((i & 31) == 0) clb[(size_t)h * nch + (i >> 5)] = std::nextafterf(static_cast<float>(suffix), -INFINITY);
+                }
+            }
+            rc = upload(&E->d_nbr, nbr.data(), nbr.size());
+            if (rc == TCSDN_OK) rc = upload(&E->d_chunk_lb, clb.data(), clb.size());
+        }
+        if (rc == TCSDN_OK) {   // scratch of a call: its own pool that keeps what it has allocated
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = m->dev;
+            TCSDN_CUDA(cudaMemPoolCreate(&E->pool, &props));
+            uint64_t keep = UINT64_MAX;
+            TCSDN_CUDA(cudaMemPoolSetAttribute(E->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
     }
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_class, tclass.data(), tclass.size());
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_row0, row0.data(), row0.size());
     if (rc == TCSDN_OK) rc = upload(&E->d_tile_rows, rows.data(), rows.size());
     if (rc == TCSDN_OK) rc = upload(&E->d_center, center.data(), center.size());
     float zero = 0.f;
-    unsigned long long zero64 = 0;
+    unsigned long long zero64[32] = {};
     if (rc == TCSDN_OK) rc = upload(&E->d_maxratio, &zero, 1);
-    if (rc == TCSDN_OK) rc = upload(&E->d_counters, &zero64, 1);
+    if (rc == TCSDN_OK) rc = upload(&E->d_counters, zero64, 32);   // [8 ..]: experiment builds' cycle counters
     m->engine = E;
     if (rc != TCSDN_OK) { engine_destroy(m); return rc; }
     return TCSDN_OK;
@@ -1204,6 +1702,9 @@ void engine_destroy(tcsdn_model *m) {
     if (!E) return;
     cudaFree(E->d_tiles); cudaFree(E->d_tile_class); cudaFree(E->d_tile_row0); cudaFree(E->d_tile_rows);
     cudaFree(E->d_center); cudaFree(E->d_refpad); cudaFree(E->d_maxratio); cudaFree(E->d_counters);
+    cudaFree(E->d_kd_dim); cudaFree(E->d_kd_child); cudaFree(E->d_kd_split); cudaFree(E->d_tcent); cudaFree(E->d_trad);
+    cudaFree(E->d_nbr); cudaFree(E->d_chunk_lb); cudaFree(E->d_ypos); cudaFree(E->d_tile_tn);
+    if (E->pool) cudaMemPoolDestroy(E->pool);
     delete E;
     m->engine = nullptr;
 }
@@ -1232,7 +1733,7 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     A.maxratio = m->opt_engine == 3 ? E->d_maxratio : nullptr;
     A.flag = flag; A.n = n; A.n_tiles = E->n_tiles;
     A.tile_bytes = E->tile_bytes; A.d = m->d; A.k = m->k; A.C = m->n_classes; A.nc1 = E->nc1;
-    A.refpad = E->d_refpad; A.dpad = (m->d + 1) & ~1;
+    A.refpad = E->d_refpad; A.dpad = kEMaxD;
     A.flush_tiles = m->opt_knn_flush > 0 ? (int)m->opt_knn_flush : kEFlushTiles;   // TCSDN_OPT_KNN_FLUSH_TILES
     A.n_ref = (int)(svc ? m->n_sv : m->n_train);
     A.g2 = static_cast<float>(-m->gamma * 1.4426950408889634);
@@ -1242,7 +1743,34 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     for (int p = 0; p < (kEMaxNC1 + 1) * kEMaxNC1 / 2; ++p) A.svc_eabs[p] = E->eabs[p];
     const bool heap_smem = !svc && m->k <= kEHeapSmemK;
     const int P = m->n_classes * (m->n_classes - 1) / 2;
-    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + 256 +
+    // KNN: order the queries by home tile (counting sort on this stream) so that a pass's 512 rows are neighbours and the
+    // producer can leave out the tiles that are too far for all of them.  Scratch comes from the engine's own stream-ordered
+    // pool (capturable into a CUDA graph, private to the call).
+    A.ypos = E->d_ypos; A.tcent = E->d_tcent; A.trad = E->d_trad; A.chunk_lb = E->d_chunk_lb; A.tile_tn = E->d_tile_tn;
+    A.nbr = nullptr; A.qperm = nullptr; A.qkey = nullptr; A.tie_list = nullptr; A.tie_count = nullptr;
+    int32_t *scratch = nullptr;
+    if (!svc) {
+        const bool prune = E->d_nbr != nullptr && m->opt_knn_prune != 1 && A.maxratio == nullptr && n < ((int64_t)1 << 31);
+        const int n_blocks = 2 * m->sm_count, n_bins = E->n_tiles;
+        const size_t n_al = ((size_t)n + 3) & ~(size_t)3;
+        // layout (int32): tie_count[4] | tie_list[n] | key[n] | perm[n] | bin_start[bins] | block_hist[blocks][bins]
+        const size_t words = 4 + n_al + (prune ? 2 * n_al + (size_t)n_bins + (size_t)n_blocks * n_bins : 0);
+        TCSDN_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), words * sizeof(int32_t), E->pool, st));
+        TCSDN_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));
+        A.tie_count = scratch;
+        A.tie_list = scratch + 4;
+        if (prune) {
+            int32_t *key = scratch + 4 + n_al, *perm = key + n_al, *bin_start = perm + n_al, *block_hist = bin_start + n_bins;
+            const int64_t rpb = (n + n_blocks - 1) / n_blocks;
+            const size_t hsm = (size_t)n_bins * sizeof(int32_t);
+            knn_key_kernel<T><<<n_blocks, kSortThreads, hsm, st>>>(x, n, m->d, rpb, E->d_kd_dim, E->d_kd_child, E->d_kd_split, n_bins, key, block_hist);
+            knn_scan_kernel<<<1, 1024, hsm, st>>>(block_hist, n_blocks, n_bins, bin_start);
+            knn_scatter_kernel<<<n_blocks, kSortThreads, hsm, st>>>(key, n, rpb, block_hist, bin_start, n_bins, perm);
+            TCSDN_CUDA(cudaGetLastError());
+            A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key;
+        }
+    }
+    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + kEBarRegion +
                         (svc ? (size_t)P * kERows * (sizeof(double) + sizeof(float))
                              : 512 * (size_t)kEListCap * sizeof(uint16_t) + (heap_smem ? 512 * (size_t)m->k * 12 : 0));
     const int64_t n_super = (n + kERows - 1) / kERows;
@@ -1276,6 +1804,12 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     m->stats[1] += n;
     // SVC: rows the certificate could not decide carry -1 - label; the fp64 kernel re-evaluates exactly those (same stream)
     if (svc && A.svc_mode == 0) return launch_svc_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, E->d_counters, st);
+    if (!svc) {   // KNN: rows whose label hangs on a tie at the k-th distance get sklearn's index-order heap (knn.cu)
+        const int rc = launch_knn_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, scores, A.tie_list, A.tie_count,
+                                         E->d_counters + 1, st);
+        TCSDN_CUDA(cudaFreeAsync(scratch, st));
+        return rc;
+    }
     return TCSDN_OK;
 }
 
@@ -1293,8 +1827,28 @@ void engine_read_stats(const tcsdn_model *m, int64_t *out) {
     if (!E) return;
     unsigned long long c = 0;
     float v = 0.f;
-    if (cudaMemcpy(&c, E->d_counters, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) out[m->kind == TCSDN_KIND_SVC ? 6 : 3] = (int64_t)c;
+    unsigned long long c4[4] = {0, 0, 0, 0};
+    if (cudaMemcpy(c4, E->d_counters, sizeof(c4), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        c = c4[0];
+        out[m->kind == TCSDN_KIND_SVC ? 6 : 3] = (int64_t)c;
+        if (m->kind != TCSDN_KIND_SVC) {   // [7] rows re-run in index order (ties), [4] reference tiles multiplied per pass x 1000
+            out[7] = (int64_t)c4[1];
+            out[4] = c4[3] ? (int64_t)(1000.0 * (double)c4[2] / (double)c4[3]) : 0;
+        }
+    }
     if (cudaMemcpy(&v, E->d_maxratio, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (int64_t)((double)v * 1099511627776.0);
+#if defined(TCSDN_EXP_KNN_TIMING)
+    unsigned long long kt[32];
+    if (cudaMemcpy(kt, E->d_counters, sizeof(kt), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        static const char *names[3] = {"producer (lane 0): aFull wait, pass setup, chunk gaps, emptyB wait", "mma warp: aFull wait, fullB wait, accEmpty wait",
+                                       "epilogue (16 lane-0s): pack, rounds, accFull wait, skipped tiles, filtered tiles, votes"};
+        for (int r = 0; r < 3; ++r) {
+            fprintf(stderr, "KT %s:", names[r]);
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %.3e", (double)kt[8 + r * 8 + i]);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
 }
 
 }  // namespace tcsdn

@@ -123,4 +123,80 @@ int launch_knn_exact(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_
     return TCSDN_OK;
 }
 
+// The tensor-core engine's tie rows (dist_engine.cu): a few rows per ten thousand whose label depends on which of several
+// equally distant training rows sklearn's index-order heap keeps.  One WARP per row: the lanes compute the distances of 32
+// consecutive training rows (the same rdist arithmetic), and the pushes happen in index order on a heap that every lane keeps
+// in step -- the sequential heap's result at 1/32 of its latency.  The number of rows is only known on the device.
+constexpr int kTieMaxD = 12;   // the engine's feature limit
+
+template <typename T>
+__global__ void __launch_bounds__(256) knn_tie_kernel(const T *__restrict__ X, int d, const double *__restrict__ fit,
+                                                      const int32_t *__restrict__ y, int64_t n_train, int k, int C,
+                                                      int32_t *__restrict__ labels, double *__restrict__ proba,
+                                                      const int32_t *__restrict__ list, const int *__restrict__ n_list,
+                                                      unsigned long long *total) {
+    const int n = *n_list;
+    if (total && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(total, (unsigned long long)n);
+    const int lane = threadIdx.x & 31;
+    const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int r = wid; r < n; r += nw) {
+        const int64_t q = list[r];
+        double qx[kTieMaxD];
+#pragma unroll
+        for (int j = 0; j < kTieMaxD; ++j) qx[j] = j < d ? static_cast<double>(X[q * d + j]) : 0.0;
+        double hv[kKnnMaxK];
+        int32_t hi[kKnnMaxK];
+        for (int s = 0; s < k; ++s) { hv[s] = DBL_MAX; hi[s] = 0; }
+        double root = DBL_MAX;
+        for (int64_t t0 = 0; t0 < n_train; t0 += 32) {
+            const int64_t t = t0 + lane;
+            double dist = DBL_MAX;
+            if (t < n_train) {
+                dist = 0.0;
+#pragma unroll
+                for (int j = 0; j < kTieMaxD; ++j)
+                    if (j < d) {
+                        const double df = __dsub_rn(qx[j], fit[t * d + j]);
+                        dist = __dadd_rn(dist, __dmul_rn(df, df));
+                    }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, dist < root);
+            while (m) {                                  // in index order; every lane performs the same push
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const double dv = __shfl_sync(0xffffffffu, dist, src);
+                if (dv < root) { heap_push_dev(hv, hi, k, dv, (int32_t)(t0 + src)); root = hv[0]; }
+            }
+        }
+        if (lane == 0) {
+            int best = 0, arg = 0;
+            for (int c = 0; c < C; ++c) {
+                int cnt = 0;
+                for (int s = 0; s < k; ++s) cnt += (y[hi[s]] == c);
+                if (proba) proba[q * C + c] = (double)cnt / (double)k;
+                if (cnt > best) { best = cnt; arg = c; }
+            }
+            labels[q] = arg;
+        }
+    }
+}
+
+int launch_knn_marked(tcsdn_model *m, const void *x, int64_t n, int dtype, int32_t *labels, double *scores,
+                      const int32_t *list, const int *count, unsigned long long *total, cudaStream_t st) {
+    if (n == 0) return TCSDN_OK;
+    if (m->d > kTieMaxD) { set_error("knn tie kernel: more than %d features", kTieMaxD); return TCSDN_EINVAL; }
+    int64_t blocks = (n + 7) / 8;                     // eight rows (warps) per block
+    const int64_t cap = (int64_t)m->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    m->stats[0] += 1;
+    if (dtype == TCSDN_F32)
+        knn_tie_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float *>(x), m->d, m->d_fit, m->d_y, m->n_train, m->k,
+                                                                m->n_classes, labels, scores, list, count, total);
+    else
+        knn_tie_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const double *>(x), m->d, m->d_fit, m->d_y, m->n_train, m->k,
+                                                                 m->n_classes, labels, scores, list, count, total);
+    TCSDN_CUDA(cudaGetLastError());
+    return TCSDN_OK;
+}
+
 }  // namespace tcsdn
