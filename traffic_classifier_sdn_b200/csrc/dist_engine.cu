@@ -123,6 +123,7 @@ constexpr float kKappa = 1.0f / 262144.0f;  // 2^-18: filter slack per unit of (
                                             // all-pairs audit observes (2^-21.0 .. 2^-20.4, tests/test_engine_gpu.py)
 constexpr int kEListCap = 24;               // per-thread candidate list, 16-bit entries (tile offset, group of 8 columns, mask)
 constexpr int kEListRoom = 8;               // one tile appends at most this many: lists are evaluated beyond cap - room
+constexpr int kEMaxLeaves = 12000;           // KNN: kd leaves = bins of the query sort (a 48 KB shared-memory histogram)
 constexpr int kEMaxPruneTiles = 4096;        // KNN: the tile-by-tile neighbour table is n_tiles^2 x 2 bytes; larger models visit every tile
 constexpr int kEFlushTiles = 31;            // default number of reference tiles between two evaluation rounds (KNN), <= 31
 
@@ -139,8 +140,10 @@ struct EngineState {
                                                // [2] KNN reference tiles multiplied (summed over passes), [3] KNN passes
     // KNN pruning (see "KNN: spatial order and pruning" in the file header)
     int32_t *d_kd_dim = nullptr;        // kd tree over the training rows: split coordinate per node, -1 = leaf
-    int32_t *d_kd_child = nullptr;      // [node][2]: children; a leaf keeps its tile in [node][0]
+    int32_t *d_kd_child = nullptr;      // [node][2]: children; a leaf keeps its number in [node][0]
     double *d_kd_split = nullptr;       // split value (rows with x[dim] < split go left)
+    int32_t *d_leaf_tile = nullptr;     // leaf -> the tile its rows sit in
+    int n_leaves = 0;
     double *d_tcent = nullptr;          // [n_tiles][d] tile centres
     double *d_trad = nullptr;           // [n_tiles] tile radii (max distance of a row from the centre, rounded up)
     uint16_t *d_nbr = nullptr;          // [n_tiles][n_tiles]: per home tile, all tiles by centre distance (nullptr: pruning off)
@@ -166,7 +169,8 @@ struct EngineArgs {
     const int32_t *y;        // KNN labels (original order; unused by the engine since the tiles are in kd order)
     const int32_t *ypos;     // KNN labels in tile order
     const int32_t *qperm;    // KNN: this call's query order (sorted by home tile) or nullptr = as given
-    const int32_t *qkey;     // KNN: home tile per query (by original index)
+    const int32_t *qkey;     // KNN: kd leaf per query (by original index)
+    const int32_t *leaf_tile;
     const double *tcent;     // KNN: tile centres / radii
     const double *trad;
     const uint16_t *nbr;     // KNN: tiles by centre distance per home tile; nullptr = visit every tile in order, skip nothing
@@ -400,9 +404,9 @@ __global__ void __launch_bounds__(kSortThreads) knn_key_kernel(const T *__restri
         int node = 0, dim;
         while ((dim = kd_dim[node]) >= 0)
             node = kd_child[2 * node + (static_cast<double>(X[i * d + dim]) < kd_split[node] ? 0 : 1)];
-        const int tile = kd_child[2 * node];
-        key[i] = tile;
-        atomicAdd(&s_hist[tile], 1);
+        const int leaf = kd_child[2 * node];
+        key[i] = leaf;
+        atomicAdd(&s_hist[leaf], 1);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_bins; i += kSortThreads) block_hist[(size_t)blockIdx.x * n_bins + i] = s_hist[i];
@@ -619,7 +623,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                 float rho = 0.f, base_up = 0.f;
                 double x0[kEMaxD];
                 if (prune) {
-                    home = A.qkey[src0];
+                    home = A.leaf_tile[A.qkey[src0]];
                     rho = __uint_as_float(*reinterpret_cast<volatile unsigned *>(&ks->rho_bits[pass & 1]));
                     double dh = 0.0;
 #pragma unroll
@@ -1428,19 +1432,26 @@ static void compact_order(const std::vector<double> &ref, int d, std::vector<int
     compact_order(ref, d, idx, mid, hi);
 }
 
-// KNN: the same ordering, recorded as a tree.  Every leaf is exactly one tile (splits fall on tile boundaries); a query row
-// descends with `x[dim] < split ? left : right` to its HOME tile (knn_key_kernel).
+// KNN: the same ordering, recorded as a tree that goes on BELOW the tiles, down to leaves of at most `leaf_rows` rows (rows may
+// be permuted freely inside a tile).  A query descends with `x[dim] < split ? left : right` to its leaf (knn_key_kernel); the
+// call sorts its queries by leaf, so the rows of a pass come from a fraction of one tile's cell, and the leaf's tile is the
+// pass's HOME tile.  Leaves are numbered in order.
 struct KdTree {
-    std::vector<int32_t> dim, child;
+    std::vector<int32_t> dim, child, leaf_tile;
     std::vector<double> split;
+    int leaf_rows = 8;
 };
 static int kd_build(const std::vector<double> &ref, int d, std::vector<int32_t> &idx, size_t lo, size_t hi, KdTree &kd) {
     const int node = (int)kd.dim.size();
     kd.dim.push_back(-1);
-    kd.child.push_back((int32_t)(lo / kEN));
+    kd.child.push_back(0);
     kd.child.push_back(0);
     kd.split.push_back(0.0);
-    if (hi - lo <= (size_t)kEN) return node;
+    if (hi - lo <= (size_t)kd.leaf_rows) {
+        kd.child[2 * (size_t)node] = (int32_t)kd.leaf_tile.size();
+        kd.leaf_tile.push_back((int32_t)(lo / kEN));
+        return node;
+    }
     int best = 0;
     double bw = -1.0;
     for (int j = 0; j < d; ++j) {
@@ -1448,7 +1459,8 @@ static int kd_build(const std::vector<double> &ref, int d, std::vector<int32_t> 
         for (size_t i = lo; i < hi; ++i) { const double v = ref[(size_t)idx[i] * d + j]; mn = std::min(mn, v); mx = std::max(mx, v); }
         if (mx - mn > bw) { bw = mx - mn; best = j; }
     }
-    const size_t mid = lo + (((hi - lo) / 2 + kEN - 1) / kEN) * kEN;   // a tile boundary, lo < mid < hi because hi - lo > 64
+    // above the tile size: split at a tile boundary (lo < mid < hi because hi - lo > 64); inside a tile: at the median
+    const size_t mid = hi - lo > (size_t)kEN ? lo + (((hi - lo) / 2 + kEN - 1) / kEN) * kEN : lo + (hi - lo) / 2;
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
                      [&](int32_t a, int32_t b2) { return ref[(size_t)a * d + best] < ref[(size_t)b2 * d + best]; });
     kd.dim[(size_t)node] = best;
@@ -1501,6 +1513,7 @@ int engine_create(tcsdn_model *m) {
     for (int64_t i = 0; i < nref; ++i) order[(size_t)i] = (int32_t)i;
     KdTree kd;
     if (!svc) {
+        while (kd.leaf_rows < kEN && nref / (kd.leaf_rows / 2 + 1) > kEMaxLeaves) kd.leaf_rows *= 2;   // the sort's histogram lives in shared memory
         kd_build(ref, d, order, 0, (size_t)nref, kd);
         for (int64_t r = 0; r < nref; r += kEN) { row0.push_back((int32_t)r); rows.push_back((int32_t)std::min<int64_t>(kEN, nref - r)); tclass.push_back(0); }
     } else {
@@ -1651,6 +1664,8 @@ int engine_create(tcsdn_model *m) {
         if (rc == TCSDN_OK) rc = upload(&E->d_kd_dim, kd.dim.data(), kd.dim.size());
         if (rc == TCSDN_OK) rc = upload(&E->d_kd_child, kd.child.data(), kd.child.size());
         if (rc == TCSDN_OK) rc = upload(&E->d_kd_split, kd.split.data(), kd.split.size());
+        if (rc == TCSDN_OK) rc = upload(&E->d_leaf_tile, kd.leaf_tile.data(), kd.leaf_tile.size());
+        E->n_leaves = (int)kd.leaf_tile.size();
         if (rc == TCSDN_OK && nt <= kEMaxPruneTiles) {
             const int nch = (nt + 31) / 32;
             std::vector<uint16_t> nbr((size_t)nt * nt);
@@ -1702,7 +1717,7 @@ void engine_destroy(tcsdn_model *m) {
     if (!E) return;
     cudaFree(E->d_tiles); cudaFree(E->d_tile_class); cudaFree(E->d_tile_row0); cudaFree(E->d_tile_rows);
     cudaFree(E->d_center); cudaFree(E->d_refpad); cudaFree(E->d_maxratio); cudaFree(E->d_counters);
-    cudaFree(E->d_kd_dim); cudaFree(E->d_kd_child); cudaFree(E->d_kd_split); cudaFree(E->d_tcent); cudaFree(E->d_trad);
+    cudaFree(E->d_kd_dim); cudaFree(E->d_kd_child); cudaFree(E->d_kd_split); cudaFree(E->d_leaf_tile); cudaFree(E->d_tcent); cudaFree(E->d_trad);
     cudaFree(E->d_nbr); cudaFree(E->d_chunk_lb); cudaFree(E->d_ypos); cudaFree(E->d_tile_tn);
     if (E->pool) cudaMemPoolDestroy(E->pool);
     delete E;
@@ -1747,11 +1762,11 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     // producer can leave out the tiles that are too far for all of them.  Scratch comes from the engine's own stream-ordered
     // pool (capturable into a CUDA graph, private to the call).
     A.ypos = E->d_ypos; A.tcent = E->d_tcent; A.trad = E->d_trad; A.chunk_lb = E->d_chunk_lb; A.tile_tn = E->d_tile_tn;
-    A.nbr = nullptr; A.qperm = nullptr; A.qkey = nullptr; A.tie_list = nullptr; A.tie_count = nullptr;
+    A.nbr = nullptr; A.qperm = nullptr; A.qkey = nullptr; A.leaf_tile = nullptr; A.tie_list = nullptr; A.tie_count = nullptr;
     int32_t *scratch = nullptr;
     if (!svc) {
         const bool prune = E->d_nbr != nullptr && m->opt_knn_prune != 1 && A.maxratio == nullptr && n < ((int64_t)1 << 31);
-        const int n_blocks = 2 * m->sm_count, n_bins = E->n_tiles;
+        const int n_blocks = 2 * m->sm_count, n_bins = E->n_leaves;
         const size_t n_al = ((size_t)n + 3) & ~(size_t)3;
         // layout (int32): tie_count[4] | tie_list[n] | key[n] | perm[n] | bin_start[bins] | block_hist[blocks][bins]
         const size_t words = 4 + n_al + (prune ? 2 * n_al + (size_t)n_bins + (size_t)n_blocks * n_bins : 0);
@@ -1767,7 +1782,7 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
             knn_scan_kernel<<<1, 1024, hsm, st>>>(block_hist, n_blocks, n_bins, bin_start);
             knn_scatter_kernel<<<n_blocks, kSortThreads, hsm, st>>>(key, n, rpb, block_hist, bin_start, n_bins, perm);
             TCSDN_CUDA(cudaGetLastError());
-            A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key;
+            A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key; A.leaf_tile = E->d_leaf_tile;
         }
     }
     const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + kEBarRegion +
