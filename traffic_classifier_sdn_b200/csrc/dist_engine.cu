@@ -102,16 +102,18 @@
 
 namespace tcsdn {
 
-constexpr int kEKnnWarps = 16;       // KNN epilogue warps (one query row per thread)
+constexpr int kEKnnWarps = 8;        // KNN epilogue warps (one query row per thread); two CTAs per SM
 constexpr int kESvcWarps = 8;        // SVC epilogue warps (two query rows per thread)
 constexpr int kEKnnThreads = (kEKnnWarps + 2) * 32;   // + producer warp + MMA warp
 constexpr int kESvcThreads = (kESvcWarps + 2) * 32;
-constexpr int kERows = 512;          // query rows per CTA pass (4 MMA tiles of 128)
+constexpr int kERows = 512;          // SVC: query rows per CTA pass (4 MMA tiles of 128)
+constexpr int kKnnRows = 256;        // KNN: query rows per CTA pass (2 MMA tiles of 128)
 constexpr int kEN = 64;              // reference rows per tile (MMA N)
 constexpr int kEK = 80;              // packed K
 constexpr int kEKSteps = kEK / 16;
 constexpr int kEMaxD = 12;           // 6 d + 6 <= 80
-constexpr int kEStages = 4;
+constexpr int kEStages = 4;          // SVC ring depth (and the size of the barrier arrays)
+constexpr int kEKnnStages = 3;       // KNN ring depth: two CTAs share the SM's shared memory
 constexpr int kETileB = kEN * kEK * 2;      // 10240 bytes of bf16 per reference tile
 constexpr int kEATile = 128 * kEK * 2;      // 20480 bytes per query tile
 constexpr int kESBO = (kEK / 8) * 128;      // 1280
@@ -217,6 +219,22 @@ __device__ __forceinline__ void e_mbar_wait(uint64_t *bar, uint32_t parity) {
     }
     __trap();
 }
+// The same wait without the suspend-time hint: with the hint a warp that arrives BEFORE the phase completes is parked, and
+// the KNN engine's warps do arrive early (most tiles are skipped or cheap) -- every tile then paid a parked warp's wake-up.
+__device__ __forceinline__ void e_mbar_poll(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(e_smem(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void e_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(e_smem(dst)),
                  "l"(src), "r"(bytes), "r"(e_smem(bar))
@@ -307,15 +325,13 @@ __device__ __forceinline__ void e_sts_v2(void *p, int2 v) {
     asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(e_smem(p)), "r"(v.x), "r"(v.y) : "memory");
 }
 
-// one padded fp64 row (12 doubles, 16-byte aligned) through the read-only path: six 16-byte loads issued back to back
+// one padded fp64 row (12 doubles = 96 bytes, 32-byte aligned) through the read-only path: three 256-bit loads (LDG.E.256) --
+// a row is three 32-byte sectors, and with scattered rows it is sector requests that the L1 runs out of: 16-byte loads cost six
 __device__ __forceinline__ void e_ldg_row12(const double *p, double (&v)[12]) {
     asm volatile(
-        "ld.global.nc.v2.f64 {%0, %1}, [%12];\n\t"
-        "ld.global.nc.v2.f64 {%2, %3}, [%12+16];\n\t"
-        "ld.global.nc.v2.f64 {%4, %5}, [%12+32];\n\t"
-        "ld.global.nc.v2.f64 {%6, %7}, [%12+48];\n\t"
-        "ld.global.nc.v2.f64 {%8, %9}, [%12+64];\n\t"
-        "ld.global.nc.v2.f64 {%10, %11}, [%12+80];"
+        "ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%12];\n\t"
+        "ld.global.nc.v4.f64 {%4, %5, %6, %7}, [%12+32];\n\t"
+        "ld.global.nc.v4.f64 {%8, %9, %10, %11}, [%12+64];"
         : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]), "=d"(v[8]), "=d"(v[9]),
           "=d"(v[10]), "=d"(v[11])
         : "l"(p));
@@ -544,14 +560,18 @@ static_assert(sizeof(KnnShared) + 256 <= kEBarRegion, "KnnShared does not fit");
 // AUDIT (SVC; KNN keeps its audit flag in NC1): a separate instantiation, because the audit indexes the accumulator registers
 // and x' dynamically, which would put them in local memory in the production kernel too
 template <typename T, bool SVC, int NC1, bool AUDIT = false>
-__global__ void __launch_bounds__(SVC ? kESvcThreads : kEKnnThreads, 1)
+__global__ void __launch_bounds__(SVC ? kESvcThreads : kEKnnThreads, SVC ? 1 : 2)
 engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int32_t *__restrict__ labels,
               double *__restrict__ scores, unsigned long long *__restrict__ counters) {
     constexpr int kEpi = SVC ? kESvcWarps : kEKnnWarps;   // epilogue warps; then the producer warp, then the MMA warp
+    constexpr int kRows = SVC ? kERows : kKnnRows;        // query rows per pass
+    constexpr int kQT = kRows / 128;                      // query tiles (MMA M = 128)
+    constexpr int kSt = SVC ? kEStages : kEKnnStages;     // ring depth
+    constexpr uint32_t kTmemCols = kQT * 2 * kEN;         // double-buffered accumulators: SVC all 512 columns, KNN 256 (two CTAs per SM)
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *sA = smem;                                          // 4 x 20480
-    unsigned char *sB = smem + 4 * kEATile;                            // kEStages x tile_bytes
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kEStages * A.tile_bytes);
+    unsigned char *sA = smem;                                          // kQT x 20480
+    unsigned char *sB = smem + kQT * kEATile;                          // kSt x tile_bytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)kSt * A.tile_bytes);
     uint64_t *fullB = bars, *emptyB = bars + kEStages, *accFull = bars + 2 * kEStages, *accEmpty = accFull + 2;
     uint64_t *aFull = accEmpty + 2;
     uint64_t *coefFree = aFull + 1;      // the epilogue warps are done with a stage's side data (SVC coefficients)
@@ -562,7 +582,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
     KnnShared *ks = reinterpret_cast<KnnShared *>(reinterpret_cast<unsigned char *>(bars) + 256);   // KNN only
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_super = (A.n + kERows - 1) / kERows;
+    const int64_t n_super = (A.n + kRows - 1) / kRows;
 
     if (tid == 0) {
         for (int s = 0; s < kEStages; ++s) {
@@ -579,7 +599,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpi + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(e_smem(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(e_smem(tmem_slot)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -615,10 +635,10 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
             KT_DECL;
             for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
                 KT_START();
-                e_mbar_wait(aFull, pass & 1);    // the pass's rows are packed, rho is known
+                e_mbar_poll(aFull, pass & 1);    // the pass's rows are packed, rho is known
                 KT_STOP(0);
                 KT_START();
-                const int64_t src0 = A.qperm ? (int64_t)A.qperm[st * kERows] : st * kERows;
+                const int64_t src0 = A.qperm ? (int64_t)A.qperm[st * kRows] : st * kRows;
                 int home = 0;
                 float rho = 0.f, base_up = 0.f;
                 double x0[kEMaxD];
@@ -685,9 +705,9 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                                 const float mgn = __fsub_rd(gi, rho);
                                 if (mgn > 0.f && __fmul_rd(mgn, mgn) > h) continue;
                             }
-                            const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                            const uint32_t s = g % kSt, ph = (g / kSt) & 1;
                             KT_START();
-                            e_mbar_wait(&emptyB[s], ph ^ 1);
+                            e_mbar_poll(&emptyB[s], ph ^ 1);
                             KT_STOP(3);
                             e_sts_v2(&ks->stageInfo[s], make_int2(ti, __float_as_int(gi)));
                             e_mbar_expect_tx(&fullB[s], (uint32_t)A.tile_bytes);
@@ -699,8 +719,8 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                     __syncwarp();
                 }
                 if (lane == 0) {                 // end of pass: an empty stage that carries -1
-                    const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
-                    e_mbar_wait(&emptyB[s], ph ^ 1);
+                    const uint32_t s = g % kSt, ph = (g / kSt) & 1;
+                    e_mbar_poll(&emptyB[s], ph ^ 1);
                     e_sts_v2(&ks->stageInfo[s], make_int2(-1, 0));
                     e_mbar_arrive(&fullB[s]);
                     ++g;
@@ -731,16 +751,16 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // SVC: every tile, in order.  KNN: whatever the producer sends, until the stage that carries -1
             for (int j = 0; SVC ? j < A.n_tiles : true; ++j, ++g) {
-                const uint32_t s = g % kEStages, ph = (g / kEStages) & 1;
+                const uint32_t s = g % kSt, ph = (g / kSt) & 1;
                 const uint32_t b = g & 1, bph = (g >> 1) & 1;
                 KT_START();
-                e_mbar_wait(&fullB[s], ph);
+                if constexpr (SVC) e_mbar_wait(&fullB[s], ph); else e_mbar_poll(&fullB[s], ph);
                 KT_STOP(1);
                 int2 info = make_int2(0, 0);
                 if constexpr (!SVC) info = e_lds_v2(&ks->stageInfo[s]);
                 const bool last = !SVC && info.x < 0;
                 KT_START();
-                e_mbar_wait(&accEmpty[b], bph ^ 1);
+                if constexpr (SVC) e_mbar_wait(&accEmpty[b], bph ^ 1); else e_mbar_poll(&accEmpty[b], bph ^ 1);
                 KT_STOP(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (e_elect_one()) {
@@ -748,7 +768,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                     if (!last) {
                         const uint32_t b_lo = ((e_smem(sB + (size_t)s * A.tile_bytes) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
+                        for (int t = 0; t < kQT; ++t) {
                             const uint32_t dcol = tmem_base + (uint32_t)((t * 2 + b) * kEN);
 #pragma unroll
 #if defined(TCSDN_EXP_NO_MMA)     // experiment build: no MMA at all (commits only)
@@ -783,7 +803,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
         KT_DECL;
         for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x, ++pass) {
             KT_START();
-            const int64_t slot = st * kERows + qt * 128 + rt;
+            const int64_t slot = st * kRows + qt * 128 + rt;
             const bool live = slot < A.n;
             const int64_t row = !live ? 0 : (A.qperm ? (int64_t)A.qperm[slot] : slot);   // the query this thread owns
             float xp_unused[kEMaxD];
@@ -791,7 +811,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
             // distance from the pass's first row (the producer's reference point), rounded up; its maximum over the pass is rho
             float e_up = 0.f;
             if (prune) {
-                const int64_t src0 = (int64_t)A.qperm[st * kERows];
+                const int64_t src0 = (int64_t)A.qperm[st * kRows];
                 double e2 = 0.0;
 #pragma unroll
                 for (int jj = 0; jj < kEMaxD; ++jj)
@@ -831,12 +851,12 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                 // memory.  Its root and the filter threshold stay in registers.
                 constexpr bool kHeapSmem = (NC1 & 1) != 0;      // KNN instantiations: NC1 bit 0 = heap in shared memory,
                 constexpr bool kAudit = (NC1 & 2) != 0;         //                     bit 1 = audit mode (error statistic)
-                constexpr int ST = kHeapSmem ? 512 : 1;
+                constexpr int ST = kHeapSmem ? kKnnRows : 1;
                 double hv_local[kHeapSmem ? 1 : kEMaxK];
                 int32_t hi_local[kHeapSmem ? 1 : kEMaxK];
-                unsigned char *heap_base = cand + 512 * kEListCap * sizeof(uint16_t);
+                unsigned char *heap_base = cand + kKnnRows * kEListCap * sizeof(uint16_t);
                 double *hv = kHeapSmem ? reinterpret_cast<double *>(heap_base) + tid : hv_local;
-                int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(heap_base + 512 * (size_t)A.k * sizeof(double)) + tid : hi_local;
+                int32_t *hi = kHeapSmem ? reinterpret_cast<int32_t *>(heap_base + kKnnRows * (size_t)A.k * sizeof(double)) + tid : hi_local;
                 for (int i = 0; i < A.k; ++i) { hv[i * ST] = DBL_MAX; hi[i * ST] = 0; }
                 double hv0 = DBL_MAX, tie_val = -1.0;
                 int tie_cls = -1;
@@ -929,7 +949,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                     const uint32_t b = g & 1, bph = (g >> 1) & 1;
                     ++g;
                     KT_START();
-                    e_mbar_wait(&accFull[b], bph);
+                    e_mbar_poll(&accFull[b], bph);
                     KT_STOP(2);
                     KT_START();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1065,7 +1085,10 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                         }
                         labels[row] = arg;
                     }
-                    if (counters) atomicAdd(counters, n_exact);
+                }
+                {   // one counter update per warp
+                    const unsigned wsum = __reduce_add_sync(0xffffffffu, live ? (unsigned)n_exact : 0u);
+                    if (lane == 0 && counters) atomicAdd(counters, (unsigned long long)wsum);
                 }
                 KT_STOP(5);
             }
@@ -1379,7 +1402,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == kEpi + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (warp == kEpi + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1785,11 +1808,12 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
             A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key; A.leaf_tile = E->d_leaf_tile;
         }
     }
-    const size_t smem = 4 * (size_t)kEATile + (size_t)kEStages * E->tile_bytes + kEBarRegion +
+    const int rows_per_pass = svc ? kERows : kKnnRows;
+    const size_t smem = (size_t)(rows_per_pass / 128) * kEATile + (size_t)(svc ? kEStages : kEKnnStages) * E->tile_bytes + kEBarRegion +
                         (svc ? (size_t)P * kERows * (sizeof(double) + sizeof(float))
-                             : 512 * (size_t)kEListCap * sizeof(uint16_t) + (heap_smem ? 512 * (size_t)m->k * 12 : 0));
-    const int64_t n_super = (n + kERows - 1) / kERows;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_super, m->sm_count);
+                             : kKnnRows * (size_t)kEListCap * sizeof(uint16_t) + (heap_smem ? kKnnRows * (size_t)m->k * 12 : 0));
+    const int64_t n_super = (n + rows_per_pass - 1) / rows_per_pass;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_super, (int64_t)m->sm_count * (svc ? 1 : 2));
 #define TCSDN_LAUNCH(SVCF, NC)                                                                                    \
     {                                                                                                             \
         auto kern = (SVCF && A.maxratio) ? engine_kernel<T, SVCF, NC, SVCF> : engine_kernel<T, SVCF, NC, false>;   \
