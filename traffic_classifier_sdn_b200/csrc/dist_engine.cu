@@ -1805,6 +1805,7 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
             knn_scan_kernel<<<1, 1024, hsm, st>>>(block_hist, n_blocks, n_bins, bin_start);
             knn_scatter_kernel<<<n_blocks, kSortThreads, hsm, st>>>(key, n, rpb, block_hist, bin_start, n_bins, perm);
             TCSDN_CUDA(cudaGetLastError());
+            m->stats[0] += 3;
             A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key; A.leaf_tile = E->d_leaf_tile;
         }
     }
