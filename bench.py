@@ -119,7 +119,7 @@ def _build_workload(name, quick=False):
         spec = dict(kind="knn", fit_X=Xtr, y=ytr.astype(np.int32), k=5, classes=synth.CLASSES, n_features=12)
         return dict(spec=spec, sk=None, d=12, rows=10_000_000 if not quick else 200_000, bytes_per_row=52,
                     flops_per_row=2 * 12 * 50_000, issued_mma_flops_per_row=2 * 80 * 64 * ((50_000 + 63) // 64),
-                    desc="KNeighbors k=5 brute force, 10M queries x 50k train rows "
+                    desc="KNeighbors k=5 (sklearn's brute-force neighbour votes; the engine prunes far tiles exactly), 10M queries x 50k train rows "
                     "(BASELINE configs[2])", bound="tensor", cpu_sample_rows=20_000)
     if name == "svc":
         # a real libsvm fit (sklearn.svm.SVC(), defaults: C=1, gamma='scale') on synthetic flows, sized so that
@@ -809,7 +809,8 @@ def main():
                 r = measure_gpu(wx, steps_x, 3, world, device, peaks, extras_light=True)
                 entry = {"workload": wx["desc"], "dtype": DTYPES.get(wx["spec"]["kind"]), "value": r["value"], "unit": "flow-rows/s", "rows_per_gpu_per_step": r["rows"],
                          "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
-                         "gpu_launches_per_step": r["launches_per_step"], "engine_stats": r["est"].stats().tolist()}
+                         "gpu_launches_per_step": r["launches_per_step"], "engine_stats": r["est"].stats().tolist(),
+                         "timed_region": r["mode"]}
                 if rank == 0 and world == 1 and not args.gpu_only:
                     entry["cpu_baseline"] = cpu_reference(wx, max_seconds=8.0)
                 vbar = (entry.get("cpu_baseline") or {}).get("node_visits_per_row") or wx.get("visits_per_row")

@@ -125,6 +125,23 @@ def test_knn_engine_pruned_equals_unpruned_and_oracle(nt, nq, k):
         assert seen[0][0] < 0.8 * n_tiles, "clustered flow rows, dense queries: the pruned pass should leave tiles out"
 
 
+def test_knn_engine_large_model_without_tile_table():
+    """beyond 4 096 tiles (262 144 training rows) there is no tile-by-tile neighbour table: the producer walks outwards from the
+    home tile in kd order and tests every tile -- same answers, still far fewer tiles than all of them"""
+    nt, nq, k = 270_000, 4096, 5
+    spec = _knn_spec(nt, k=k, seed=99)
+    Xq = synth.make_flows(nq, seed=123, return_labels=False)
+    Xq[:50] = spec["fit_X"][:50]
+    est = _force(from_spec(spec), 2)
+    idx, pr = est._run(Xq, True)
+    ridx, rpr = oracle.knn(spec, Xq)
+    st = est.stats()
+    assert st[1] == nq and np.array_equal(idx, ridx) and np.array_equal(pr, rpr)
+    n_tiles = -(-nt // 64)
+    print(f"knn nt={nt}: {st[4] / 1000:.1f} of {n_tiles} tiles per pass, {st[3] / nq:.1f} exact evaluations per query, {st[7]} tie rows")
+    assert st[4] / 1000.0 < 0.5 * n_tiles
+
+
 def test_knn_engine_class_relevant_ties_go_to_index_order_kernel():
     """twin training rows with DIFFERENT classes and k = 1: the label is whichever twin sklearn's heap keeps (the first); twins
     with the SAME class need no second opinion"""

@@ -65,7 +65,7 @@
 // boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows in tile order
 // (even row stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.  Pruning tables:
 // tile centres and radii (fp64), the kd tree, and per home tile the list of all tiles by centre distance (n_tiles^2 x 2 B,
-// 1.2 MB at 782 tiles; models beyond 4096 tiles visit every tile).
+// 1.2 MB at 782 tiles; models beyond 4096 tiles walk outwards from the home tile in kd order and test every tile).
 //
 // Kernel (persistent, 1 CTA / SM).  A CTA owns 512 query rows at a time:
 //   KNN: warps 0-15, each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
@@ -175,7 +175,7 @@ struct EngineArgs {
     const int32_t *leaf_tile;
     const double *tcent;     // KNN: tile centres / radii
     const double *trad;
-    const uint16_t *nbr;     // KNN: tiles by centre distance per home tile; nullptr = visit every tile in order, skip nothing
+    const uint16_t *nbr;     // KNN: tiles by centre distance per home tile; nullptr = walk outwards from the home tile in kd order
     const float *chunk_lb;
     const float *tile_tn;    // KNN: per tile, the largest centred squared norm of its rows
     int32_t *tie_list;       // KNN: rows whose label needs the index-order heap (ties at the k-th distance across classes)
@@ -628,7 +628,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
             // (x0 = first row of the pass, rho = largest ||x - x0|| in the pass, H = largest current k-th distance^2 in the pass;
             // H only falls, so a test that passes with a stale H stays valid).  Lanes compute the 32 gaps of a chunk in fp64, lane 0
             // walks the chunk with the current H and loads what survives; a chunk-level bound ends the pass early.
-            const bool prune = A.nbr != nullptr && A.qperm != nullptr;
+            const bool prune = A.qperm != nullptr;
             const int n_chunks = (A.n_tiles + 31) >> 5;
             uint32_t g = 0, pass = 0;            // g is lane 0's
             unsigned long long n_mult = 0;
@@ -664,7 +664,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                 for (int c = 0; c < n_chunks; ++c) {
                     KT_START();
                     const float current_h_all = prune ? current_h() : 0.f;
-                    if (prune) {                 // everything from this chunk on is farther than H from every row of the pass
+                    if (prune && A.nbr) {        // everything from this chunk on is farther than H from every row of the pass
                         const float mgn = __fsub_rd(A.chunk_lb[(size_t)home * n_chunks + c], base_up);
                         if (mgn > 0.f && __fmul_rd(mgn, mgn) > current_h_all) break;
                     }
@@ -672,7 +672,16 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
                     const bool valid = t < A.n_tiles;
                     float gap = -FLT_MAX;
                     if (prune && valid) {
-                        t = A.nbr[(size_t)home * A.n_tiles + t];
+                        if (A.nbr) {
+                            t = A.nbr[(size_t)home * A.n_tiles + t];
+                        } else {
+                            // no tile-by-tile table (models beyond kEMaxPruneTiles): neighbours in kd order are neighbours in
+                            // space, so walk outwards from the home tile -- home, +1, -1, +2, -2, ... then what is left of the
+                            // longer side; every tile is tested (no early end of the pass)
+                            const int lo = home, hi = A.n_tiles - 1 - home, mside = min(lo, hi);
+                            if (t <= 2 * mside) { const int kk = (t + 1) >> 1; t = (t & 1) ? home + kk : home - kk; }
+                            else { const int jj = t - 2 * mside; t = hi > lo ? home + mside + jj : home - mside - jj; }
+                        }
                         double dd = 0.0;
 #pragma unroll
                         for (int jj = 0; jj < kEMaxD; ++jj) {
@@ -797,7 +806,7 @@ engine_kernel(const __grid_constant__ EngineArgs A, const T *__restrict__ X, int
         const int qt = warp >> 2;                           // query tile 0..3
         const int rt = (warp & 3) * 32 + lane;              // row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const bool prune = A.nbr != nullptr && A.qperm != nullptr;
+        const bool prune = A.qperm != nullptr;
         uint32_t g = 0, pass = 0;
         float nf = 0.f;
         KT_DECL;
@@ -1788,8 +1797,9 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     A.nbr = nullptr; A.qperm = nullptr; A.qkey = nullptr; A.leaf_tile = nullptr; A.tie_list = nullptr; A.tie_count = nullptr;
     int32_t *scratch = nullptr;
     if (!svc) {
-        const bool prune = E->d_nbr != nullptr && m->opt_knn_prune != 1 && A.maxratio == nullptr && n < ((int64_t)1 << 31);
         const int n_blocks = 2 * m->sm_count, n_bins = E->n_leaves;
+        const size_t hsm = (size_t)n_bins * sizeof(int32_t);   // the sort's histogram: shared memory
+        const bool prune = m->opt_knn_prune != 1 && A.maxratio == nullptr && n < ((int64_t)1 << 31) && hsm <= 200 * 1024;
         const size_t n_al = ((size_t)n + 3) & ~(size_t)3;
         // layout (int32): tie_count[4] | tie_list[n] | key[n] | perm[n] | bin_start[bins] | block_hist[blocks][bins]
         const size_t words = 4 + n_al + (prune ? 2 * n_al + (size_t)n_bins + (size_t)n_blocks * n_bins : 0);
@@ -1800,13 +1810,18 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
         if (prune) {
             int32_t *key = scratch + 4 + n_al, *perm = key + n_al, *bin_start = perm + n_al, *block_hist = bin_start + n_bins;
             const int64_t rpb = (n + n_blocks - 1) / n_blocks;
-            const size_t hsm = (size_t)n_bins * sizeof(int32_t);
+            if (hsm > 48 * 1024) {
+                TCSDN_CUDA(cudaFuncSetAttribute(knn_key_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                TCSDN_CUDA(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                TCSDN_CUDA(cudaFuncSetAttribute(knn_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+            }
             knn_key_kernel<T><<<n_blocks, kSortThreads, hsm, st>>>(x, n, m->d, rpb, E->d_kd_dim, E->d_kd_child, E->d_kd_split, n_bins, key, block_hist);
             knn_scan_kernel<<<1, 1024, hsm, st>>>(block_hist, n_blocks, n_bins, bin_start);
             knn_scatter_kernel<<<n_blocks, kSortThreads, hsm, st>>>(key, n, rpb, block_hist, bin_start, n_bins, perm);
             TCSDN_CUDA(cudaGetLastError());
             m->stats[0] += 3;
-            A.nbr = E->d_nbr; A.qperm = perm; A.qkey = key; A.leaf_tile = E->d_leaf_tile;
+            A.nbr = E->d_nbr;   // nullptr beyond kEMaxPruneTiles: the producer walks outwards in kd order instead
+            A.qperm = perm; A.qkey = key; A.leaf_tile = E->d_leaf_tile;
         }
     }
     const int rows_per_pass = svc ? kERows : kKnnRows;

@@ -148,24 +148,34 @@ __global__ void __launch_bounds__(256) knn_tie_kernel(const T *__restrict__ X, i
         int32_t hi[kKnnMaxK];
         for (int s = 0; s < k; ++s) { hv[s] = DBL_MAX; hi[s] = 0; }
         double root = DBL_MAX;
-        for (int64_t t0 = 0; t0 < n_train; t0 += 32) {
-            const int64_t t = t0 + lane;
-            double dist = DBL_MAX;
-            if (t < n_train) {
-                dist = 0.0;
+        // 64 training rows per step: two independent distance chains per lane (the loop is bound by the latency of the loads
+        // and of the fp64 chain), the two groups of 32 offered to the heap in index order
+        for (int64_t t0 = 0; t0 < n_train; t0 += 64) {
+            double dist[2];
 #pragma unroll
-                for (int j = 0; j < kTieMaxD; ++j)
-                    if (j < d) {
-                        const double df = __dsub_rn(qx[j], fit[t * d + j]);
-                        dist = __dadd_rn(dist, __dmul_rn(df, df));
-                    }
+            for (int u = 0; u < 2; ++u) {
+                const int64_t t = t0 + 32 * u + lane;
+                dist[u] = DBL_MAX;
+                if (t < n_train) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < kTieMaxD; ++j)
+                        if (j < d) {
+                            const double df = __dsub_rn(qx[j], fit[t * d + j]);
+                            acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        }
+                    dist[u] = acc;
+                }
             }
-            unsigned m = __ballot_sync(0xffffffffu, dist < root);
-            while (m) {                                  // in index order; every lane performs the same push
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const double dv = __shfl_sync(0xffffffffu, dist, src);
-                if (dv < root) { heap_push_dev(hv, hi, k, dv, (int32_t)(t0 + src)); root = hv[0]; }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                unsigned m = __ballot_sync(0xffffffffu, dist[u] < root);
+                while (m) {                              // in index order; every lane performs the same push
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double dv = __shfl_sync(0xffffffffu, dist[u], src);
+                    if (dv < root) { heap_push_dev(hv, hi, k, dv, (int32_t)(t0 + 32 * u + src)); root = hv[0]; }
+                }
             }
         }
         if (lane == 0) {
