@@ -130,8 +130,12 @@ def test_knn_engine_large_model_without_tile_table():
     home tile in kd order and tests every tile -- same answers, still far fewer tiles than all of them"""
     nt, nq, k = 270_000, 4096, 5
     spec = _knn_spec(nt, k=k, seed=99)
-    Xq = synth.make_flows(nq, seed=123, return_labels=False)
-    Xq[:50] = spec["fit_X"][:50]
+    # 16 spots x 256 queries around them: with 4 219 kd cells, 4 096 queries spread over the whole feature space would put one
+    # query in each cell and leave a pass nothing to leave out
+    rng = np.random.default_rng(123)
+    spots = spec["fit_X"][rng.choice(nt, 16, replace=False)]
+    Xq = (spots[:, None, :] * (1.0 + 1e-3 * rng.standard_normal((16, 256, 12))) + 1e-2 * rng.standard_normal((16, 256, 12))).reshape(nq, 12)
+    Xq[::256] = spots                                        # the spots themselves: distance 0 to a training row
     est = _force(from_spec(spec), 2)
     idx, pr = est._run(Xq, True)
     ridx, rpr = oracle.knn(spec, Xq)
