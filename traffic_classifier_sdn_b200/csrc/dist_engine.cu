@@ -1795,6 +1795,11 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     // pool (capturable into a CUDA graph, private to the call).
     A.ypos = E->d_ypos; A.tcent = E->d_tcent; A.trad = E->d_trad; A.chunk_lb = E->d_chunk_lb; A.tile_tn = E->d_tile_tn;
     A.nbr = nullptr; A.qperm = nullptr; A.qkey = nullptr; A.leaf_tile = nullptr; A.tie_list = nullptr; A.tie_count = nullptr;
+    struct ScratchGuard {   // the call's scratch goes back to the pool behind everything enqueued so far, on every return path
+        int32_t *p = nullptr;
+        cudaStream_t st = nullptr;
+        ~ScratchGuard() { if (p) cudaFreeAsync(p, st); }
+    } scratch_guard;
     int32_t *scratch = nullptr;
     if (!svc) {
         const int n_blocks = 2 * m->sm_count, n_bins = E->n_leaves;
@@ -1804,6 +1809,8 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
         // layout (int32): tie_count[4] | tie_list[n] | key[n] | perm[n] | bin_start[bins] | block_hist[blocks][bins]
         const size_t words = 4 + n_al + (prune ? 2 * n_al + (size_t)n_bins + (size_t)n_blocks * n_bins : 0);
         TCSDN_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), words * sizeof(int32_t), E->pool, st));
+        scratch_guard.p = scratch;
+        scratch_guard.st = st;
         TCSDN_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), st));
         A.tie_count = scratch;
         A.tie_list = scratch + 4;
@@ -1860,10 +1867,8 @@ static int launch_engine_t(tcsdn_model *m, const T *x, int64_t n, int32_t *label
     // SVC: rows the certificate could not decide carry -1 - label; the fp64 kernel re-evaluates exactly those (same stream)
     if (svc && A.svc_mode == 0) return launch_svc_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, E->d_counters, st);
     if (!svc) {   // KNN: rows whose label hangs on a tie at the k-th distance get sklearn's index-order heap (knn.cu)
-        const int rc = launch_knn_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, scores, A.tie_list, A.tie_count,
-                                         E->d_counters + 1, st);
-        TCSDN_CUDA(cudaFreeAsync(scratch, st));
-        return rc;
+        return launch_knn_marked(m, x, n, sizeof(T) == 4 ? TCSDN_F32 : TCSDN_F64, labels, scores, A.tie_list, A.tie_count,
+                                 E->d_counters + 1, st);
     }
     return TCSDN_OK;
 }
