@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <new>
 #include <thread>
+#include <type_traits>
 
 #include "common.h"
 
@@ -570,10 +571,33 @@ int tcsdn_take_labels(const int32_t *idx, int64_t n, const void *table, int32_t 
     if (n_threads > 64) n_threads = 64;
     if ((int64_t)n_threads > n / 65536 + 1) n_threads = (int32_t)(n / 65536 + 1);
     std::atomic<int> bad{0};
+    // fixed-width labels are short ('<U6' = 24 bytes): a memcpy CALL per row costs more than the copy, so widths that are a
+    // multiple of eight move as 64-bit words with the width known to the compiler (8 / 16 / 24 / 32 bytes), others fall back
+    const bool words = item_bytes % 8 == 0 && item_bytes <= 32 && (reinterpret_cast<uintptr_t>(table) % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(out) % 8 == 0);
     auto work = [&](int64_t lo, int64_t hi) {
         const char *tab = static_cast<const char *>(table);
         char *o = static_cast<char *>(out);
         const size_t w = (size_t)item_bytes;
+        if (words) {
+            const uint64_t *t64 = static_cast<const uint64_t *>(table);
+            uint64_t *o64 = static_cast<uint64_t *>(out);
+            auto run = [&](auto wc) {
+                constexpr int W = decltype(wc)::value;
+                for (int64_t i = lo; i < hi; ++i) {
+                    const int32_t k = idx[i];
+                    if (k < 0 || k >= n_items) { bad.store(1); return; }
+                    for (int j = 0; j < W; ++j) o64[i * W + j] = t64[(int64_t)k * W + j];
+                }
+            };
+            switch (item_bytes / 8) {
+                case 1: run(std::integral_constant<int, 1>{}); break;
+                case 2: run(std::integral_constant<int, 2>{}); break;
+                case 3: run(std::integral_constant<int, 3>{}); break;
+                default: run(std::integral_constant<int, 4>{}); break;
+            }
+            return;
+        }
         for (int64_t i = lo; i < hi; ++i) {
             const int32_t k = idx[i];
             if (k < 0 || k >= n_items) { bad.store(1); return; }
