@@ -62,23 +62,25 @@
 // canonical K-major / no-swizzle layout (8x8 core matrices of 128 B; LBO = 128 B along K, SBO = 1280 B along N),
 // followed (SVC) by the tile's dual coefficients [C-1][64] fp32, its centre c'_j and the two constants of eta_j.  A tile image is contiguous in HBM, so
 // one cp.async.bulk (TMA unit, UBLKCP) brings it into a shared-memory ring stage.  SVC classes start on tile
-// boundaries (padded with zero-coefficient rows).  KNN keeps a second, padded fp64 copy of the training rows in tile order
-// (even row stride: 16-byte loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and stays in L2.  Pruning tables:
-// tile centres and radii (fp64), the kd tree, and per home tile the list of all tiles by centre distance (n_tiles^2 x 2 B,
-// 1.2 MB at 782 tiles; models beyond 4096 tiles walk outwards from the home tile in kd order and test every tile).
+// boundaries (padded with zero-coefficient rows).  KNN keeps a second fp64 copy of the training rows in tile order, padded to
+// 12 doubles (three 32-byte sectors, read with three 256-bit loads) for the exact re-evaluation; at 50k x 12 it is 4.8 MB and
+// stays in L2.  Pruning tables: tile centres and radii (fp64), the kd tree, and per home tile the list of all tiles by centre
+// distance (n_tiles^2 x 2 B, 1.2 MB at 782 tiles; models beyond 4096 tiles walk outwards from the home tile in kd order and
+// test every tile).
 //
-// Kernel (persistent, 1 CTA / SM).  A CTA owns 512 query rows at a time:
-//   KNN: warps 0-15, each thread owns ONE query row: packs it into the A operand (4 tiles of 128 x 80 bf16 in shared
+// Kernel (persistent).  SVC: 1 CTA / SM, 512 query rows per pass.  KNN: 2 CTAs / SM, 256 query rows per pass.
+//   KNN: warps 0-7, each thread owns ONE query row: packs it into the A operand (2 tiles of 128 x 80 bf16 in shared
 //               memory, same canonical layout), later reads its accumulator row from TMEM (tcgen05.ld 32x32b)
 //               and runs the filter epilogue on 64 columns per reference tile;
 //   SVC: warps 0-7, each thread owns TWO query rows (the same TMEM lane of two query tiles), so that one broadcast
 //               LDS.128 of dual coefficients feeds two rows: the coefficient loads were the kernel's bound (shared-memory
 //               return bandwidth, profiles/r01e), not the ex2 unit;
-//   next warp   one lane streams reference tile images through a 4-stage ring (bulk copy + mbarrier tx count);
-//   last warp   runs warp-uniformly; one ELECTED lane issues 4 (query tiles) x 5 (K steps) tcgen05.mma M128 N64 K16 per
-//               reference tile into a double-buffered TMEM accumulator (4 tiles x 2 buffers x 64 columns = all 512
-//               columns) and commits to the ring's "empty" barrier and the accumulator's "full" barrier.
-// Each reference tile (10 KB) is reused by 512 query rows: 16 B/clk/SM of L2 traffic against 640 clk of MMA.
+//   next warp   streams reference tile images through a 4-stage (KNN: 3-stage) ring (bulk copy + mbarrier tx count); SVC: every
+//               tile in order, one lane; KNN: the whole warp computes which tiles the pass needs (see above), lane 0 loads them;
+//   last warp   runs warp-uniformly; one ELECTED lane issues 5 (K steps) tcgen05.mma M128 N64 K16 per query tile and reference
+//               tile into a double-buffered TMEM accumulator (query tiles x 2 buffers x 64 columns: SVC all 512 columns, KNN 256
+//               per CTA) and commits to the ring's "empty" barrier and the accumulator's "full" barrier.
+// Each reference tile (10 KB) is reused by all query rows of the pass.
 //
 // A hazard worth writing down (it cost a debugging session on the B200): an mbarrier.arrive does NOT wait for the
 // warp's outstanding ld.shared.  The SVC epilogue reads the dual coefficients out of the ring stage with plain
